@@ -1,0 +1,12 @@
+"""gaussianavatars_b200 -- B200-native (sm_100a) differentiable Gaussian-splat rasterizer with the GaussianAvatars
+FLAME mesh binding fused into preprocess.  Drop-in for the `diff_gaussian_rasterization` operator behind
+gaussian_renderer.render() (reference: gaussian_renderer/__init__.py:15,37-52,86-94).
+
+Nothing here falls back to CPU or eager PyTorch: the ops raise if libgaussianavatars_b200.so is missing.
+"""
+from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, rasterize_bound,
+                         bind_activate, set_exact_binning)
+from .renderer import render, render_bound
+
+__all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_bound",
+           "bind_activate", "set_exact_binning", "render", "render_bound"]

@@ -1,0 +1,181 @@
+"""ctypes binding of libgaussianavatars_b200.so (the C ABI of include/gab200_rasterizer.h).
+
+There is NO fallback: if the shared library is missing or fails to load, importing the ops raises.  PyTorch is
+used only for device memory (the allocation callbacks hand out torch uint8 tensors), streams and autograd glue.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgaussianavatars_b200.so")
+
+ABI_VERSION = 1
+INPUT_ACTIVATED = 0
+INPUT_BOUND_RAW = 1
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+
+class ForwardArgs(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("input_mode", C.c_int32), ("P", C.c_int32), ("sh_degree", C.c_int32),
+        ("sh_coeffs", C.c_int32), ("image_width", C.c_int32), ("image_height", C.c_int32),
+        ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_backward", C.c_int32), ("exact_binning", C.c_int32),
+        ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+        ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
+        ("cov3D_precomp", C.c_void_p), ("shs", C.c_void_p), ("sh_dc", C.c_void_p), ("sh_rest", C.c_void_p),
+        ("colors_precomp", C.c_void_p),
+        ("binding", C.c_void_p), ("num_faces", C.c_int32), ("face_center", C.c_void_p),
+        ("face_orien_mat", C.c_void_p), ("face_scaling", C.c_void_p),
+        ("out_color", C.c_void_p), ("radii", C.c_void_p),
+        ("alloc_geom", ALLOC_FN), ("alloc_binning", ALLOC_FN), ("alloc_image", ALLOC_FN), ("alloc_user", C.c_void_p),
+    ]
+
+
+class FrameState(C.Structure):
+    _fields_ = [
+        ("num_rendered", C.c_int64), ("num_candidates", C.c_int64),
+        ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("image_buffer", C.c_void_p),
+        ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t), ("image_bytes", C.c_size_t),
+        ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32),
+    ]
+
+
+class BackwardArgs(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("fwd", C.POINTER(ForwardArgs)), ("state", C.POINTER(FrameState)),
+        ("dL_dout_color", C.c_void_p), ("dL_dmeans3D", C.c_void_p), ("dL_dmeans2D", C.c_void_p),
+        ("dL_dopacity", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dsh_dc", C.c_void_p),
+        ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
+        ("dL_dcov3D", C.c_void_p), ("dL_dface_center", C.c_void_p), ("dL_dface_orien_mat", C.c_void_p),
+        ("dL_dface_scaling", C.c_void_p),
+    ]
+
+
+EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
+                    "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version")
+
+_lib = None
+_lock = threading.Lock()
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the CUDA library.  Raises NativeLibraryError (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise NativeLibraryError(
+                f"{LIB_PATH} not found: build it with `python -m gaussianavatars_b200.build` "
+                "(or __graft_entry__.build()).  gaussianavatars_b200 has no CPU / eager fallback.")
+        try:
+            L = C.CDLL(LIB_PATH)
+        except OSError as e:  # pragma: no cover
+            raise NativeLibraryError(f"cannot load {LIB_PATH}: {e}") from e
+        for s in EXPORTED_SYMBOLS:
+            if not hasattr(L, s):
+                raise NativeLibraryError(f"{LIB_PATH} does not export {s}")
+        L.gab200_forward.restype = C.c_int64
+        L.gab200_forward.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p]
+        L.gab200_backward.restype = C.c_int32
+        L.gab200_backward.argtypes = [C.POINTER(BackwardArgs), C.c_void_p]
+        L.gab200_mark_visible.restype = C.c_int32
+        L.gab200_mark_visible.argtypes = [C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gab200_bind_activate.restype = C.c_int32
+        L.gab200_bind_activate.argtypes = [C.POINTER(ForwardArgs), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]
+        L.gab200_export_binning.restype = C.c_int32
+        L.gab200_export_binning.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p, C.c_void_p,
+                                            C.c_void_p, C.c_void_p]
+        L.gab200_launch_count.restype = C.c_int64
+        L.gab200_status_string.restype = C.c_char_p
+        L.gab200_status_string.argtypes = [C.c_int32]
+        L.gab200_abi_version.restype = C.c_uint32
+        if L.gab200_abi_version() != ABI_VERSION:
+            raise NativeLibraryError("ABI version mismatch between _native.py and the shared library")
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str):
+    if status < 0:
+        msg = lib().gab200_status_string(int(status)).decode()
+        raise RuntimeError(f"{what} failed: {msg} (status {status})")
+    return status
+
+
+def launch_count() -> int:
+    return int(lib().gab200_launch_count())
+
+
+# ---- scratch allocation: the reference's three resizable byte buffers, as torch uint8 tensors -------------------
+class _Scratch(threading.local):
+    holder = None   # list receiving the tensors of the forward in flight on this thread
+    device = None
+
+
+_scratch = _Scratch()
+
+
+def _alloc_cb(user, nbytes):
+    t = torch.empty(max(int(nbytes), 1), dtype=torch.uint8, device=_scratch.device)
+    _scratch.holder.append(t)
+    return t.data_ptr()
+
+
+ALLOC_CALLBACK = ALLOC_FN(_alloc_cb)  # one C thunk for the whole process (kept alive here)
+
+
+class _InferencePool:
+    """no_grad renders reuse three growing buffers per device instead of allocating per frame."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def get(self, device, slot, nbytes):
+        key = (device, slot)
+        t = self.bufs.get(key)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(int(nbytes * 1.25) + 256, dtype=torch.uint8, device=device)
+            self.bufs[key] = t
+        return t
+
+
+_pool = _InferencePool()
+_pool_slot = threading.local()
+
+
+def _alloc_pooled_cb(user, nbytes):
+    slot = _pool_slot.next
+    _pool_slot.next = slot + 1
+    return _pool.get(_scratch.device, slot, max(int(nbytes), 1)).data_ptr()
+
+
+ALLOC_POOLED_CALLBACK = ALLOC_FN(_alloc_pooled_cb)
+
+
+def begin_forward(device, need_backward: bool):
+    """Returns (callback, holder).  holder keeps the per-call scratch alive for backward (None when pooled)."""
+    _scratch.device = device
+    if need_backward:
+        _scratch.holder = []
+        return ALLOC_CALLBACK, _scratch.holder
+    _pool_slot.next = 0
+    return ALLOC_POOLED_CALLBACK, None
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()

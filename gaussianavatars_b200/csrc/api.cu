@@ -1,0 +1,288 @@
+// api.cu -- the extern "C" boundary declared in include/gab200_rasterizer.h.  Host orchestration only: argument
+// validation, carving of the three caller-allocated byte buffers, stage launches, the single host sync that sizes
+// the binning buffer.  No torch types, no exceptions, no global state beyond a launch counter.
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace gab {
+static std::atomic<int64_t> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct GeomView {
+  SplatRec* rec;
+  uint32_t* tiles_touched;
+  uint32_t* offsets;
+  uint8_t* clamped;
+  float* g2d;
+  void* scan_temp;
+  size_t scan_temp_bytes;
+  size_t bytes;
+};
+static GeomView carve_geom(void* base, int P, bool need_backward) {
+  GeomView g;
+  Carver c(base);
+  g.rec = c.take<SplatRec>((size_t)P);
+  g.tiles_touched = c.take<uint32_t>((size_t)P);
+  g.offsets = c.take<uint32_t>((size_t)P);
+  g.clamped = c.take<uint8_t>((size_t)P);
+  g.g2d = need_backward ? c.take<float>((size_t)P * GAB_G2D_STRIDE) : nullptr;
+  g.scan_temp_bytes = scan_temp_bytes(P);
+  g.scan_temp = c.take<char>(g.scan_temp_bytes);
+  g.bytes = c.bytes();
+  return g;
+}
+struct BinView {
+  uint64_t* keys[2];
+  uint32_t* vals[2];
+  void* sort_temp;
+  size_t sort_temp_bytes;
+  size_t bytes;
+};
+static BinView carve_binning(void* base, int64_t N, int sort_bits) {
+  BinView b;
+  Carver c(base);
+  const size_t n = (size_t)(N > 0 ? N : 1);
+  b.keys[0] = c.take<uint64_t>(n);
+  b.keys[1] = c.take<uint64_t>(n);
+  b.vals[0] = c.take<uint32_t>(n);
+  b.vals[1] = c.take<uint32_t>(n);
+  b.sort_temp_bytes = sort_temp_bytes(N > 0 ? N : 1, sort_bits);
+  b.sort_temp = c.take<char>(b.sort_temp_bytes);
+  b.bytes = c.bytes();
+  return b;
+}
+struct ImageView {
+  uint2* ranges;
+  float* final_T;
+  uint32_t* n_contrib;
+  size_t bytes;
+};
+static ImageView carve_image(void* base, int W, int H, bool need_backward) {
+  ImageView v;
+  Carver c(base);
+  const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
+  v.ranges = c.take<uint2>((size_t)gx * gy);
+  v.final_T = need_backward ? c.take<float>((size_t)W * H) : nullptr;
+  v.n_contrib = need_backward ? c.take<uint32_t>((size_t)W * H) : nullptr;
+  v.bytes = c.bytes();
+  return v;
+}
+
+static int check_arch() {
+  static std::atomic<int> cached{0};  // 0 unknown, 1 ok, -1 bad
+  int c = cached.load();
+  if (c != 0) return c;
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
+  c = (major == 10) ? 1 : -1;
+  cached.store(c);
+  return c;
+}
+
+static bool validate(const gab200_forward_args* a) {
+  if (a == nullptr || a->abi_version != GAB200_ABI_VERSION) return false;
+  if (a->P < 0 || a->image_width <= 0 || a->image_height <= 0) return false;
+  if (a->out_color == nullptr || (a->P > 0 && a->radii == nullptr)) return false;
+  if (!a->bg || !a->viewmatrix || !a->projmatrix || !a->campos) return false;
+  if (!a->alloc_geom || !a->alloc_binning || !a->alloc_image) return false;
+  if (a->P == 0) return true;
+  if (!a->means3D || !a->opacities) return false;
+  if (a->sh_degree < 0 || a->sh_degree > 3) return false;
+  const int nb = (a->sh_degree + 1) * (a->sh_degree + 1);
+  if (a->input_mode == GAB200_INPUT_ACTIVATED) {
+    const bool has_sr = a->scales != nullptr && a->rotations != nullptr;
+    if (has_sr == (a->cov3D_precomp != nullptr)) return false;  // exactly one of (scale,rot) / cov3D
+    if ((a->scales != nullptr) != (a->rotations != nullptr)) return false;
+    if ((a->shs != nullptr) == (a->colors_precomp != nullptr)) return false;  // exactly one of SH / colours
+    if (a->shs != nullptr && a->sh_coeffs < nb) return false;
+  } else if (a->input_mode == GAB200_INPUT_BOUND_RAW) {
+    if (!a->scales || !a->rotations || a->cov3D_precomp) return false;
+    if (a->colors_precomp == nullptr) {
+      if (!a->sh_dc || a->sh_coeffs < nb) return false;
+      if (a->sh_coeffs > 1 && !a->sh_rest) return false;
+    }
+    if (a->binding != nullptr && (!a->face_center || !a->face_orien_mat || !a->face_scaling || a->num_faces <= 0))
+      return false;
+  } else {
+    return false;
+  }
+  return true;
+}
+
+#define GAB_CUDA(expr)                                  \
+  do {                                                  \
+    cudaError_t _e = (expr);                            \
+    if (_e != cudaSuccess) return GAB200_ERR_CUDA;      \
+  } while (0)
+#define GAB_STAGE_CHECK(dbg, stream)                                  \
+  do {                                                                \
+    if (cudaPeekAtLastError() != cudaSuccess) return GAB200_ERR_CUDA; \
+    if (dbg) GAB_CUDA(cudaStreamSynchronize(stream));                 \
+  } while (0)
+
+}  // namespace gab
+
+using namespace gab;
+
+extern "C" {
+
+uint32_t gab200_abi_version(void) { return GAB200_ABI_VERSION; }
+int64_t gab200_launch_count(void) { return g_launches.load(); }
+
+const char* gab200_status_string(int32_t s) {
+  switch (s) {
+    case GAB200_OK: return "ok";
+    case GAB200_ERR_INVALID_ARGUMENT: return "invalid argument (shape / missing pointer / inconsistent options)";
+    case GAB200_ERR_CUDA: return "CUDA runtime or kernel error";
+    case GAB200_ERR_ALLOC: return "allocation callback returned NULL";
+    case GAB200_ERR_ARCH: return "device is not sm_100 class (this library ships sm_100a code only)";
+    case GAB200_ERR_OVERFLOW: return "instance count overflows 32 bits";
+    default: return "unknown status";
+  }
+}
+
+int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!validate(a) || st == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  memset(st, 0, sizeof(*st));
+  const int P = a->P, W = a->image_width, H = a->image_height;
+  const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
+  const bool nb = a->need_backward != 0;
+  const bool dbg = a->debug != 0;
+
+  // ---- geometry + image buffers ----
+  GeomView gsz = carve_geom(nullptr, P, nb);
+  void* geom = a->alloc_geom(a->alloc_user, gsz.bytes);
+  if (geom == nullptr) return GAB200_ERR_ALLOC;
+  GeomView g = carve_geom(geom, P, nb);
+  ImageView isz = carve_image(nullptr, W, H, nb);
+  void* img = a->alloc_image(a->alloc_user, isz.bytes);
+  if (img == nullptr) return GAB200_ERR_ALLOC;
+  ImageView iv = carve_image(img, W, H, nb);
+  st->geom_buffer = geom; st->geom_bytes = g.bytes;
+  st->image_buffer = img; st->image_bytes = iv.bytes;
+  st->sort_bits = 32 + (int)tile_bits((uint32_t)(gx * gy));
+
+  int64_t N = 0;
+  if (P > 0) {
+    launch_preprocess(*a, g.rec, g.tiles_touched, nb ? g.clamped : nullptr, stream);
+    GAB_STAGE_CHECK(dbg, stream);
+    GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.offsets, P, stream));
+    GAB_STAGE_CHECK(dbg, stream);
+    uint32_t n_host = 0;
+    GAB_CUDA(cudaMemcpyAsync(&n_host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GAB_CUDA(cudaStreamSynchronize(stream));
+    N = (int64_t)n_host;
+  }
+  st->num_rendered = N;
+  st->num_candidates = N;
+
+  BinView bsz = carve_binning(nullptr, N, st->sort_bits);
+  void* bin = a->alloc_binning(a->alloc_user, bsz.bytes);
+  if (bin == nullptr) return GAB200_ERR_ALLOC;
+  BinView bv = carve_binning(bin, N, st->sort_bits);
+  st->binning_buffer = bin; st->binning_bytes = bv.bytes;
+
+  GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+  int selector = 0;
+  if (N > 0) {
+    launch_emit_keys(P, gx, gy, g.rec, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+    GAB_STAGE_CHECK(dbg, stream);
+    GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], N,
+                      st->sort_bits, &selector, stream));
+    GAB_STAGE_CHECK(dbg, stream);
+    launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
+    GAB_STAGE_CHECK(dbg, stream);
+  }
+  st->sorted_selector = selector;
+  launch_blend_forward(W, H, iv.ranges, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
+                       stream);
+  GAB_STAGE_CHECK(dbg, stream);
+  return N;
+}
+
+int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (b == nullptr || b->abi_version != GAB200_ABI_VERSION || b->fwd == nullptr || b->state == nullptr)
+    return GAB200_ERR_INVALID_ARGUMENT;
+  const gab200_forward_args* a = b->fwd;
+  const gab200_frame_state* st = b->state;
+  if (!validate(a) || !a->need_backward || b->dL_dout_color == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
+  if (st->geom_buffer == nullptr || st->image_buffer == nullptr || st->binning_buffer == nullptr)
+    return GAB200_ERR_INVALID_ARGUMENT;
+  const int P = a->P, W = a->image_width, H = a->image_height;
+  const bool dbg = a->debug != 0;
+  const bool bound = a->input_mode == GAB200_INPUT_BOUND_RAW;
+  if (bound && a->colors_precomp == nullptr && (b->dL_dsh_dc == nullptr || (a->sh_coeffs > 1 && b->dL_dsh_rest == nullptr)))
+    return GAB200_ERR_INVALID_ARGUMENT;
+  if (P == 0) return GAB200_OK;
+  GeomView g = carve_geom(st->geom_buffer, P, true);
+  ImageView iv = carve_image(st->image_buffer, W, H, true);
+  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits);
+
+  GAB_CUDA(cudaMemsetAsync(g.g2d, 0, sizeof(float) * (size_t)P * GAB_G2D_STRIDE, stream));
+  if (bound && a->binding != nullptr) {
+    const size_t F = (size_t)a->num_faces;
+    if (b->dL_dface_center) GAB_CUDA(cudaMemsetAsync(b->dL_dface_center, 0, sizeof(float) * 3 * F, stream));
+    if (b->dL_dface_orien_mat) GAB_CUDA(cudaMemsetAsync(b->dL_dface_orien_mat, 0, sizeof(float) * 9 * F, stream));
+    if (b->dL_dface_scaling) GAB_CUDA(cudaMemsetAsync(b->dL_dface_scaling, 0, sizeof(float) * F, stream));
+  }
+  if (bound && a->colors_precomp != nullptr) {
+    if (b->dL_dsh_dc) GAB_CUDA(cudaMemsetAsync(b->dL_dsh_dc, 0, sizeof(float) * 3 * (size_t)P, stream));
+    if (b->dL_dsh_rest && a->sh_coeffs > 1)
+      GAB_CUDA(cudaMemsetAsync(b->dL_dsh_rest, 0, sizeof(float) * 3 * (size_t)(a->sh_coeffs - 1) * P, stream));
+  }
+  if (st->num_rendered > 0) {
+    launch_blend_backward(W, H, iv.ranges, bv.vals[st->sorted_selector], g.rec, a->bg, iv.final_T, iv.n_contrib,
+                          b->dL_dout_color, g.g2d, stream);
+    GAB_STAGE_CHECK(dbg, stream);
+  }
+  launch_preprocess_backward(*b, g.rec, g.clamped, g.g2d, stream);
+  GAB_STAGE_CHECK(dbg, stream);
+  return GAB200_OK;
+}
+
+int32_t gab200_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                            uint8_t* present, void* stream_) {
+  (void)projmatrix;
+  if (P < 0 || (P > 0 && (!means3D || !viewmatrix || !present))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  launch_mark_visible(P, means3D, viewmatrix, present, (cudaStream_t)stream_);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_bind_activate(const gab200_forward_args* a, float* means3D, float* opacities, float* scales,
+                             float* cov3D, void* stream_) {
+  if (a == nullptr || a->abi_version != GAB200_ABI_VERSION || a->input_mode != GAB200_INPUT_BOUND_RAW || a->P < 0)
+    return GAB200_ERR_INVALID_ARGUMENT;
+  if (a->P > 0 && (!a->means3D || !a->opacities || !a->scales || !a->rotations)) return GAB200_ERR_INVALID_ARGUMENT;
+  if (a->binding != nullptr && (!a->face_center || !a->face_orien_mat || !a->face_scaling))
+    return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  launch_bind_activate(*a, means3D, opacities, scales, cov3D, (cudaStream_t)stream_);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_state* st, uint64_t* keys,
+                              uint32_t* values, uint32_t* ranges, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (a == nullptr || st == nullptr || st->binning_buffer == nullptr || st->image_buffer == nullptr)
+    return GAB200_ERR_INVALID_ARGUMENT;
+  const int W = a->image_width, H = a->image_height;
+  const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
+  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits);
+  ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
+  const size_t N = (size_t)st->num_rendered;
+  if (keys && N) GAB_CUDA(cudaMemcpyAsync(keys, bv.keys[st->sorted_selector], 8 * N, cudaMemcpyDeviceToDevice, stream));
+  if (values && N) GAB_CUDA(cudaMemcpyAsync(values, bv.vals[st->sorted_selector], 4 * N, cudaMemcpyDeviceToDevice, stream));
+  if (ranges) GAB_CUDA(cudaMemcpyAsync(ranges, iv.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));
+  return GAB200_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Internal launcher declarations + small device helpers shared by the .cu files.
+#pragma once
+#include "common.cuh"
+
+namespace gab {
+
+// SH constants (values of utils/sh_utils.py:26-43)
+#define SH_C0 0.28209479177387814f
+#define SH_C1 0.4886025119029199f
+#define SH_C2_0 1.0925484305920792f
+#define SH_C2_1 -1.0925484305920792f
+#define SH_C2_2 0.31539156525252005f
+#define SH_C2_3 -1.0925484305920792f
+#define SH_C2_4 0.5462742152960396f
+#define SH_C3_0 -0.5900435899266435f
+#define SH_C3_1 2.890611442640554f
+#define SH_C3_2 -0.4570457994644658f
+#define SH_C3_3 0.3731763325901154f
+#define SH_C3_4 -0.4570457994644658f
+#define SH_C3_5 1.445305721320277f
+#define SH_C3_6 -0.5900435899266435f
+
+void count_launch();
+
+// Exact per-tile-row span of the region where a splat can reach alpha >= 1/255:
+//   q(d) = 1/2 (A dx^2 + C dy^2) + B dx dy <= ln(255 * opacity)          (the blend's own accept test)
+// For tile row ty the pixel centres have dy in [16 ty - py, 16 ty + 15 - py]; the x-extent of the ellipse over
+// that band is closed-form (extreme point if it lies in the band, else the better band edge).  The span is
+// intersected with the reference's 3-sigma bounding-square columns [rx0, rx1) so the emitted instance list is
+// always a SUBSEQUENCE of the reference's.  Margins: +0.01 in the exponent (alpha down to 0.99/255 kept) and
+// +-0.02 px, i.e. only pairs that contribute exactly nothing are dropped.
+struct TileSpan {
+  bool any, full;
+  float px, py, A, B, tau2A, det, dxmax, ystar, ymax;
+  int rx0, rx1;
+  __device__ __forceinline__ TileSpan(float px_, float py_, float A_, float B_, float C_, float opacity, int rx0_,
+                                      int rx1_)
+      : px(px_), py(py_), A(A_), B(B_), rx0(rx0_), rx1(rx1_) {
+    const float tau = logf(255.f * opacity) + 0.01f;
+    det = A_ * C_ - B_ * B_;
+    const bool pd = (det > 0.f) && (A_ > 0.f) && (C_ > 0.f) && (det < 3.0e38f);
+    any = tau > 0.f;
+    full = !pd || !(tau < 3.0e38f);
+    const float tau2 = 2.f * tau;
+    tau2A = tau2 * A_;
+    dxmax = sqrtf(fmaxf(0.f, tau2 * C_ / det));
+    ymax = sqrtf(fmaxf(0.f, tau2 * A_ / det));
+    ystar = (B_ / C_) * dxmax;
+  }
+  __device__ __forceinline__ float half_width(float dy) const { return sqrtf(fmaxf(0.f, tau2A - det * dy * dy)); }
+  __device__ __forceinline__ void row(int ty, int& cx0, int& cx1) const {
+    if (!any) { cx0 = cx1 = rx0; return; }
+    if (full) { cx0 = rx0; cx1 = rx1; return; }
+    const float a = (float)(ty * GAB_TILE) - py, b = a + (float)(GAB_TILE - 1);
+    const float lo = fmaxf(a, -ymax) - 0.02f, hi = fminf(b, ymax) + 0.02f;
+    if (lo > hi) { cx0 = cx1 = rx0; return; }
+    float xr, xl;
+    const float hl = half_width(lo), hh = half_width(hi);
+    if (-ystar >= lo && -ystar <= hi) xr = dxmax;
+    else xr = fmaxf((-B * lo + hl) / A, (-B * hi + hh) / A);
+    if (ystar >= lo && ystar <= hi) xl = -dxmax;
+    else xl = fminf((-B * lo - hl) / A, (-B * hi - hh) / A);
+    const float X0 = px + xl - 0.02f, X1 = px + xr + 0.02f;
+    int t0 = (int)ceilf((X0 - (float)(GAB_TILE - 1)) * (1.0f / GAB_TILE));
+    int t1 = (int)floorf(X1 * (1.0f / GAB_TILE)) + 1;
+    cx0 = min(max(t0, rx0), rx1);
+    cx1 = max(min(t1, rx1), cx0);
+  }
+};
+
+// ---- launchers (each counts its launches) ----
+void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, uint32_t* tiles_touched, uint8_t* clamped,
+                       cudaStream_t stream);
+void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
+                          cudaStream_t stream);
+void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
+void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const uint32_t* offsets, uint64_t* keys,
+                      uint32_t* vals, int exact_binning, cudaStream_t stream);
+void launch_tile_ranges(int64_t N, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+
+// binning.cu (cub)
+size_t scan_temp_bytes(int P);
+cudaError_t run_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P, cudaStream_t stream);
+size_t sort_temp_bytes(int64_t N, int end_bit);
+cudaError_t run_sort(void* temp, size_t temp_bytes, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a,
+                     uint32_t* vals_b, int64_t N, int end_bit, int* selector_out, cudaStream_t stream);
+
+// blend.cu
+void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+                          const float* bg, float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream);
+void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+                           const float* bg, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
+                           float* g2d, cudaStream_t stream);
+
+// preprocess_bwd.cu
+void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const uint8_t* clamped,
+                                const float* g2d, cudaStream_t stream);
+
+}  // namespace gab

@@ -1,0 +1,154 @@
+// splat_math.cuh -- device math shared by preprocess.cu (compiled --fmad=false, bit-reproducible) and
+// preprocess_bwd.cu (default contraction).  Each translation unit gets its own copy under its own flags.
+#pragma once
+#include "common.cuh"
+#include "kernels.cuh"
+
+namespace gab {
+
+__device__ __forceinline__ float3 xform4x3(const float* M, float3 p) {
+  float3 r;
+  r.x = M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12];
+  r.y = M[1] * p.x + M[5] * p.y + M[9] * p.z + M[13];
+  r.z = M[2] * p.x + M[6] * p.y + M[10] * p.z + M[14];
+  return r;
+}
+
+__device__ __forceinline__ float ndc2pix(float v, int S) {
+  return (float)((((double)v + 1.0) * (double)S - 1.0) * 0.5);
+}
+
+__device__ __forceinline__ void tile_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0, int& x1,
+                                          int& y1) {
+  x0 = min(gx, max(0, (int)((px - (float)radius) / (float)GAB_TILE)));
+  y0 = min(gy, max(0, (int)((py - (float)radius) / (float)GAB_TILE)));
+  x1 = min(gx, max(0, (int)((px + (float)radius + (float)(GAB_TILE - 1)) / (float)GAB_TILE)));
+  y1 = min(gy, max(0, (int)((py + (float)radius + (float)(GAB_TILE - 1)) / (float)GAB_TILE)));
+}
+
+__device__ __forceinline__ void quat_to_R(float r, float x, float y, float z, float R[9]) {
+  R[0] = 1.f - 2.f * (y * y + z * z);
+  R[1] = 2.f * (x * y - r * z);
+  R[2] = 2.f * (x * z + r * y);
+  R[3] = 2.f * (x * y + r * z);
+  R[4] = 1.f - 2.f * (x * x + z * z);
+  R[5] = 2.f * (y * z - r * x);
+  R[6] = 2.f * (x * z - r * y);
+  R[7] = 2.f * (y * z + r * x);
+  R[8] = 1.f - 2.f * (x * x + y * y);
+}
+
+// Sigma = R diag(s^2) R^T from a rotation matrix and s (already multiplied by scale_modifier)
+__device__ __forceinline__ void cov3d_from_R(const float R[9], const float s[3], float cov[6]) {
+  float M[9];
+#pragma unroll
+  for (int k = 0; k < 3; k++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) M[3 * k + i] = s[k] * R[3 * i + k];
+  cov[0] = M[0] * M[0] + M[3] * M[3] + M[6] * M[6];
+  cov[1] = M[0] * M[1] + M[3] * M[4] + M[6] * M[7];
+  cov[2] = M[0] * M[2] + M[3] * M[5] + M[6] * M[8];
+  cov[3] = M[1] * M[1] + M[4] * M[4] + M[7] * M[7];
+  cov[4] = M[1] * M[2] + M[4] * M[5] + M[7] * M[8];
+  cov[5] = M[2] * M[2] + M[5] * M[5] + M[8] * M[8];
+}
+
+// ---- the binding + activation of scene/gaussian_model.py:113-160, shared by forward / export / backward ----
+struct Activated {
+  float3 mean;     // world position
+  float opacity;   // sigmoid
+  float s[3];      // exp(_scaling) * face_scaling          (WITHOUT scale_modifier)
+  float R[9];      // world rotation R_face * R(normalize(_rotation))
+};
+// intermediates the backward chain needs (dead code in the forward instantiation)
+struct BindCtx {
+  float3 xl;       // raw local position
+  float qn[4];     // normalised local quaternion (wxyz)
+  float nrm;       // max(|q|, 1e-12)
+  float e[3];      // exp(_scaling)
+  float fs;        // face scale (1 when unbound)
+  float Rf[9];     // face frame (identity when unbound)
+  float Rl[9];     // R(qn)
+  float3 rx;       // R_face * xl
+  int face;        // -1 when unbound
+};
+
+__device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, Activated& o, BindCtx& c) {
+  c.xl = make_float3(a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]);
+  // rotation_activation = torch.nn.functional.normalize (eps 1e-12)
+  float qr = a.rotations[4 * (size_t)i], qx = a.rotations[4 * (size_t)i + 1], qy = a.rotations[4 * (size_t)i + 2],
+        qz = a.rotations[4 * (size_t)i + 3];
+  float n = sqrtf(qr * qr + qx * qx + qy * qy + qz * qz);
+  n = fmaxf(n, 1e-12f);
+  c.nrm = n;
+  c.qn[0] = qr / n; c.qn[1] = qx / n; c.qn[2] = qy / n; c.qn[3] = qz / n;
+  quat_to_R(c.qn[0], c.qn[1], c.qn[2], c.qn[3], c.Rl);
+  c.e[0] = expf(a.scales[3 * (size_t)i]);
+  c.e[1] = expf(a.scales[3 * (size_t)i + 1]);
+  c.e[2] = expf(a.scales[3 * (size_t)i + 2]);
+  o.opacity = 1.0f / (1.0f + expf(-a.opacities[i]));
+  if (a.binding != nullptr) {
+    const int f = a.binding[i];
+    c.face = f;
+    const float* Rf = a.face_orien_mat + 9 * (size_t)f;
+    c.fs = a.face_scaling[f];
+    const float* fc = a.face_center + 3 * (size_t)f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) c.Rf[k] = Rf[k];
+    // get_xyz: bmm(R_face, x) * s + c
+    c.rx.x = c.Rf[0] * c.xl.x + c.Rf[1] * c.xl.y + c.Rf[2] * c.xl.z;
+    c.rx.y = c.Rf[3] * c.xl.x + c.Rf[4] * c.xl.y + c.Rf[5] * c.xl.z;
+    c.rx.z = c.Rf[6] * c.xl.x + c.Rf[7] * c.xl.y + c.Rf[8] * c.xl.z;
+    o.mean = make_float3(c.rx.x * c.fs + fc[0], c.rx.y * c.fs + fc[1], c.rx.z * c.fs + fc[2]);
+    o.s[0] = c.e[0] * c.fs; o.s[1] = c.e[1] * c.fs; o.s[2] = c.e[2] * c.fs;
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int cc = 0; cc < 3; cc++)
+        o.R[3 * r + cc] = c.Rf[3 * r + 0] * c.Rl[0 + cc] + c.Rf[3 * r + 1] * c.Rl[3 + cc] + c.Rf[3 * r + 2] * c.Rl[6 + cc];
+  } else {
+    c.face = -1;
+    c.fs = 1.f;
+#pragma unroll
+    for (int k = 0; k < 9; k++) c.Rf[k] = (k % 4 == 0) ? 1.f : 0.f;
+    c.rx = c.xl;
+    o.mean = c.xl;
+    o.s[0] = c.e[0]; o.s[1] = c.e[1]; o.s[2] = c.e[2];
+#pragma unroll
+    for (int k = 0; k < 9; k++) o.R[k] = c.Rl[k];
+  }
+}
+__device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, Activated& o) {
+  BindCtx c;
+  bind_activate(a, i, o, c);
+}
+
+__device__ __forceinline__ void sh_basis(int deg, float3 d, float B[16]) {
+  B[0] = SH_C0;
+  if (deg > 0) {
+    float x = d.x, y = d.y, z = d.z;
+    B[1] = -SH_C1 * y;
+    B[2] = SH_C1 * z;
+    B[3] = -SH_C1 * x;
+    if (deg > 1) {
+      float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+      B[4] = SH_C2_0 * xy;
+      B[5] = SH_C2_1 * yz;
+      B[6] = SH_C2_2 * (2.0f * zz - xx - yy);
+      B[7] = SH_C2_3 * xz;
+      B[8] = SH_C2_4 * (xx - yy);
+      if (deg > 2) {
+        B[9] = SH_C3_0 * y * (3.0f * xx - yy);
+        B[10] = SH_C3_1 * xy * z;
+        B[11] = SH_C3_2 * y * (4.0f * zz - xx - yy);
+        B[12] = SH_C3_3 * z * (2.0f * zz - 3.0f * xx - 3.0f * yy);
+        B[13] = SH_C3_4 * x * (4.0f * zz - xx - yy);
+        B[14] = SH_C3_5 * z * (xx - yy);
+        B[15] = SH_C3_6 * x * (xx - 3.0f * yy);
+      }
+    }
+  }
+}
+
+
+}  // namespace gab

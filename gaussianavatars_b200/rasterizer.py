@@ -1,0 +1,365 @@
+"""Host-side mirror of the reference operator surface, backed by the sm_100a C-ABI library.
+
+Drop-in names (the only two GaussianAvatars imports, gaussian_renderer/__init__.py:15):
+    GaussianRasterizationSettings, GaussianRasterizer
+with the semantics of diff_gaussian_rasterization/__init__.py of the pinned submodule:
+same argument names, same "exactly one of" exceptions, same outputs (color (3,H,W), radii (P,) int32), same
+gradient tuple (means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, None).
+
+New, opt-in fused surface (SURVEY.md 8b "Fused surface"): `rasterize_bound(...)` takes the RAW GaussianModel
+parameters plus the per-face frame and runs scene/gaussian_model.py:113-160 inside the preprocess kernel; its
+backward returns gradients for the raw parameters and for face_center / face_orien_mat / face_scaling.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool
+
+
+# Binning policy of the library (include/gab200_rasterizer.h `exact_binning`).  False (default) drops (splat, tile)
+# pairs that provably contribute nothing; image, radii and gradients are unchanged.  True reproduces the
+# reference's full 3-sigma bounding-square instance list (used by the key/sort parity tests).
+_EXACT_BINNING = False
+
+
+def set_exact_binning(flag: bool):
+    global _EXACT_BINNING
+    _EXACT_BINNING = bool(flag)
+
+
+def _f32c(t: Optional[torch.Tensor], name: str, device):
+    if t is None or t.numel() == 0:
+        return None
+    if t.device != device:
+        raise ValueError(f"{name} must live on {device}, got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _cam(t: torch.Tensor, name: str, device):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError(f"{name} must be a tensor")
+    if t.device != device or t.dtype != torch.float32:
+        t = t.to(device=device, dtype=torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P: int, need_backward: bool):
+    a.abi_version = N.ABI_VERSION
+    a.P = P
+    a.sh_degree = int(rs.sh_degree)
+    a.image_width = int(rs.image_width)
+    a.image_height = int(rs.image_height)
+    a.tanfovx = float(rs.tanfovx)
+    a.tanfovy = float(rs.tanfovy)
+    a.scale_modifier = float(rs.scale_modifier)
+    a.prefiltered = int(bool(rs.prefiltered))
+    a.debug = int(bool(rs.debug))
+    a.need_backward = int(need_backward)
+    a.exact_binning = int(_EXACT_BINNING)
+    cams = (_cam(rs.bg, "bg", device), _cam(rs.viewmatrix, "viewmatrix", device),
+            _cam(rs.projmatrix, "projmatrix", device), _cam(rs.campos, "campos", device))
+    a.bg, a.viewmatrix, a.projmatrix, a.campos = (t.data_ptr() for t in cams)
+    return cams
+
+
+_KEEP_LAST = False
+_last = None
+
+
+def keep_last_state(flag: bool):
+    """Parity/debug hook: retain the last forward's scratch so `export_last_binning()` can read the sorted stream."""
+    global _KEEP_LAST, _last
+    _KEEP_LAST = bool(flag)
+    if not flag:
+        _last = None
+
+
+def export_last_binning():
+    """(keys u64 as int64 tensor, values int32 tensor, ranges (tiles,2) int32 tensor, num_rendered) of the last forward."""
+    if _last is None:
+        raise RuntimeError("keep_last_state(True) was not set before the forward")
+    a, st, holder, device = _last
+    n = int(st.num_rendered)
+    gx, gy = (a.image_width + 15) // 16, (a.image_height + 15) // 16
+    keys = torch.empty((max(n, 1),), dtype=torch.int64, device=device)
+    vals = torch.empty((max(n, 1),), dtype=torch.int32, device=device)
+    ranges = torch.empty((gx * gy, 2), dtype=torch.int32, device=device)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        N.check(N.lib().gab200_export_binning(C.byref(a), C.byref(st), keys.data_ptr(), vals.data_ptr(),
+                                              ranges.data_ptr(), C.c_void_p(stream)), "gab200_export_binning")
+    return keys[:n], vals[:n], ranges, n
+
+
+def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
+    H, W, P = a.image_height, a.image_width, a.P
+    color = torch.empty((3, H, W), dtype=torch.float32, device=device)
+    radii = torch.empty((P,), dtype=torch.int32, device=device)
+    a.out_color, a.radii = color.data_ptr(), radii.data_ptr()
+    cb, holder = N.begin_forward(device, need_backward)
+    a.alloc_geom = a.alloc_binning = a.alloc_image = cb
+    st = N.FrameState()
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        n = N.lib().gab200_forward(C.byref(a), C.byref(st), C.c_void_p(stream))
+    N.check(n, "gab200_forward")
+    if _KEEP_LAST:
+        global _last
+        # pooled (inference) scratch stays valid until the next no_grad forward on this device
+        _last = (a, st, holder, device)
+    return color, radii, st, holder
+
+
+class _RasterizeGaussians(torch.autograd.Function):
+    """Reference surface (ACTIVATED inputs)."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                raster_settings):
+        rs = raster_settings
+        device = means3D.device
+        if device.type != "cuda":
+            raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
+        if means3D.ndim != 2 or means3D.shape[1] != 3:
+            raise RuntimeError("means3D must have dimensions (num_points, 3)")
+        P = means3D.shape[0]
+        need_bw = any(ctx.needs_input_grad)
+        a = N.ForwardArgs()
+        cams = _fill_common(a, rs, device, P, need_bw)
+        a.input_mode = N.INPUT_ACTIVATED
+        means3D = _f32c(means3D, "means3D", device)
+        sh = _f32c(sh, "shs", device)
+        colors_precomp = _f32c(colors_precomp, "colors_precomp", device)
+        opacities = _f32c(opacities, "opacities", device)
+        scales = _f32c(scales, "scales", device)
+        rotations = _f32c(rotations, "rotations", device)
+        cov3Ds_precomp = _f32c(cov3Ds_precomp, "cov3D_precomp", device)
+        a.sh_coeffs = 0 if sh is None else sh.shape[1]
+        a.means3D, a.opacities = N.ptr(means3D), N.ptr(opacities)
+        a.scales, a.rotations, a.cov3D_precomp = N.ptr(scales), N.ptr(rotations), N.ptr(cov3Ds_precomp)
+        a.shs, a.colors_precomp = N.ptr(sh), N.ptr(colors_precomp)
+        color, radii, st, holder = _run_forward(a, device, need_bw)
+        if need_bw:
+            ctx.args, ctx.state, ctx.holder = a, st, holder
+            ctx.keep = (cams, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, radii)
+            ctx.M = a.sh_coeffs
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        a, st = ctx.args, ctx.state
+        cams, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, radii = ctx.keep
+        device = means3D.device
+        P, M = a.P, ctx.M
+        g = grad_out_color if grad_out_color.is_contiguous() else grad_out_color.contiguous()
+        e = lambda *s: torch.empty(s, dtype=torch.float32, device=device)  # noqa: E731
+        d_means3D, d_means2D, d_opac = e(P, 3), e(P, 3), e(P, 1)
+        d_colors = e(P, 3)
+        d_sh = e(P, M, 3) if sh is not None else None
+        d_scales = e(P, 3) if scales is not None else None
+        d_rots = e(P, 4) if rotations is not None else None
+        d_cov = e(P, 6)
+        b = N.BackwardArgs()
+        b.abi_version = N.ABI_VERSION
+        b.fwd, b.state = C.pointer(a), C.pointer(st)
+        b.dL_dout_color = g.data_ptr()
+        b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dopacity = d_means3D.data_ptr(), d_means2D.data_ptr(), d_opac.data_ptr()
+        b.dL_dcolors, b.dL_dshs = d_colors.data_ptr(), N.ptr(d_sh)
+        b.dL_dscales, b.dL_drotations, b.dL_dcov3D = N.ptr(d_scales), N.ptr(d_rots), d_cov.data_ptr()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_backward(C.byref(b), C.c_void_p(stream)), "gab200_backward")
+        ctx.holder = None
+        return (d_means3D, d_means2D, d_sh, d_colors if colors_precomp is not None else None, d_opac, d_scales, d_rots,
+                d_cov if cov3Ds_precomp is not None else None, None)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings):
+    return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
+                                     cov3Ds_precomp, raster_settings)
+
+
+class GaussianRasterizer(nn.Module):
+    def __init__(self, raster_settings: GaussianRasterizationSettings):
+        super().__init__()
+        self.raster_settings = raster_settings
+
+    def markVisible(self, positions):
+        with torch.no_grad():
+            rs = self.raster_settings
+            device = positions.device
+            pos = _f32c(positions, "positions", device)
+            out = torch.empty((pos.shape[0],), dtype=torch.uint8, device=device)
+            view, proj = _cam(rs.viewmatrix, "viewmatrix", device), _cam(rs.projmatrix, "projmatrix", device)
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                N.check(N.lib().gab200_mark_visible(pos.shape[0], pos.data_ptr(), view.data_ptr(), proj.data_ptr(),
+                                                    out.data_ptr(), C.c_void_p(stream)), "gab200_mark_visible")
+        return out.bool()
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
+                                   cov3D_precomp, self.raster_settings)
+
+
+# ================================================================================================================
+# Fused surface
+# ================================================================================================================
+class _RasterizeBound(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, _xyz, means2D, _rotation, _scaling, _opacity, f_dc, f_rest, face_center, face_orien_mat,
+                face_scaling, binding, colors_precomp, raster_settings):
+        rs = raster_settings
+        device = _xyz.device
+        if device.type != "cuda":
+            raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
+        P = _xyz.shape[0]
+        need_bw = any(ctx.needs_input_grad)
+        a = N.ForwardArgs()
+        cams = _fill_common(a, rs, device, P, need_bw)
+        a.input_mode = N.INPUT_BOUND_RAW
+        _xyz, _rotation = _f32c(_xyz, "_xyz", device), _f32c(_rotation, "_rotation", device)
+        _scaling, _opacity = _f32c(_scaling, "_scaling", device), _f32c(_opacity, "_opacity", device)
+        f_dc, f_rest = _f32c(f_dc, "_features_dc", device), _f32c(f_rest, "_features_rest", device)
+        colors_precomp = _f32c(colors_precomp, "colors_precomp", device)
+        M = 1 + (0 if f_rest is None else f_rest.shape[1])
+        a.sh_coeffs = M
+        a.means3D, a.rotations, a.scales, a.opacities = _xyz.data_ptr(), _rotation.data_ptr(), _scaling.data_ptr(), \
+            _opacity.data_ptr()
+        a.sh_dc, a.sh_rest, a.colors_precomp = N.ptr(f_dc), N.ptr(f_rest), N.ptr(colors_precomp)
+        F = 0
+        if binding is not None:
+            if binding.dtype != torch.int32:
+                binding = binding.to(torch.int32)
+            binding = binding.contiguous()
+            face_center = _f32c(face_center, "face_center", device)
+            face_orien_mat = _f32c(face_orien_mat, "face_orien_mat", device)
+            face_scaling = _f32c(face_scaling, "face_scaling", device)
+            F = face_center.shape[0]
+            a.binding, a.num_faces = binding.data_ptr(), F
+            a.face_center, a.face_orien_mat, a.face_scaling = face_center.data_ptr(), face_orien_mat.data_ptr(), \
+                face_scaling.data_ptr()
+        color, radii, st, holder = _run_forward(a, device, need_bw)
+        if need_bw:
+            ctx.args, ctx.state, ctx.holder = a, st, holder
+            ctx.keep = (cams, _xyz, _rotation, _scaling, _opacity, f_dc, f_rest, face_center, face_orien_mat,
+                        face_scaling, binding, colors_precomp, radii)
+            ctx.dims = (P, M, F)
+            ctx.face_shapes = None if binding is None else (face_center.shape, face_orien_mat.shape,
+                                                            face_scaling.shape)
+        ctx.mark_non_differentiable(radii)
+        return color, radii
+
+    @staticmethod
+    def backward(ctx, grad_out_color, _grad_radii):
+        a, st = ctx.args, ctx.state
+        P, M, F = ctx.dims
+        device = ctx.keep[1].device
+        binding, colors_precomp = ctx.keep[10], ctx.keep[11]
+        g = grad_out_color if grad_out_color.is_contiguous() else grad_out_color.contiguous()
+        # one flat buffer for all per-splat parameter gradients (dist.py all-reduces it in ONE collective):
+        # [_xyz 3 | _rotation 4 | _scaling 3 | _opacity 1 | f_dc 3 | f_rest 3(M-1)]  = 59 floats/splat at SH3
+        widths = (3, 4, 3, 1, 3, 3 * (M - 1))
+        flat = torch.empty((P * sum(widths),), dtype=torch.float32, device=device)
+        views, off = [], 0
+        for w in widths:
+            views.append(flat[off:off + P * w])
+            off += P * w
+        d_xyz, d_rot, d_scale, d_opac = views[0].view(P, 3), views[1].view(P, 4), views[2].view(P, 3), views[3].view(P, 1)
+        d_dc = views[4].view(P, 1, 3)
+        d_rest = views[5].view(P, M - 1, 3) if M > 1 else None
+        d_means2D = torch.empty((P, 3), dtype=torch.float32, device=device)
+        d_colors = torch.empty((P, 3), dtype=torch.float32, device=device) if colors_precomp is not None else None
+        d_fc = d_fR = d_fs = None
+        if binding is not None:
+            fshape = ctx.face_shapes
+            d_fc = torch.empty(fshape[0], dtype=torch.float32, device=device)
+            d_fR = torch.empty(fshape[1], dtype=torch.float32, device=device)
+            d_fs = torch.empty(fshape[2], dtype=torch.float32, device=device)
+        b = N.BackwardArgs()
+        b.abi_version = N.ABI_VERSION
+        b.fwd, b.state = C.pointer(a), C.pointer(st)
+        b.dL_dout_color = g.data_ptr()
+        b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dopacity = d_xyz.data_ptr(), d_means2D.data_ptr(), d_opac.data_ptr()
+        b.dL_dcolors = N.ptr(d_colors)
+        b.dL_dsh_dc, b.dL_dsh_rest = d_dc.data_ptr(), N.ptr(d_rest)
+        b.dL_dscales, b.dL_drotations = d_scale.data_ptr(), d_rot.data_ptr()
+        b.dL_dface_center, b.dL_dface_orien_mat, b.dL_dface_scaling = N.ptr(d_fc), N.ptr(d_fR), N.ptr(d_fs)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_backward(C.byref(b), C.c_void_p(stream)), "gab200_backward")
+        ctx.holder = None
+        return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None)
+
+
+def rasterize_bound(raster_settings: GaussianRasterizationSettings, _xyz, _rotation, _scaling, _opacity,
+                    features_dc, features_rest, binding=None, face_center=None, face_orien_mat=None,
+                    face_scaling=None, means2D=None, colors_precomp=None):
+    """Fused binding + rasterization.  Returns (color (3,H,W), radii (P,) int32).
+
+    binding=None is the identity frame (a plain GaussianModel, scene/gaussian_model.py:115-116,127-128,142-143).
+    `means2D` is the usual (P,3) gradient holder (its .grad receives dL/dmean2D in NDC units)."""
+    if means2D is None:
+        means2D = torch.zeros((_xyz.shape[0], 3), dtype=torch.float32, device=_xyz.device)
+    if _opacity.ndim == 1:
+        _opacity = _opacity[:, None]
+    return _RasterizeBound.apply(_xyz, means2D, _rotation, _scaling, _opacity, features_dc, features_rest,
+                                 face_center, face_orien_mat, face_scaling, binding, colors_precomp, raster_settings)
+
+
+def bind_activate(raster_settings_or_modifier, _xyz, _rotation, _scaling, _opacity, binding=None, face_center=None,
+                  face_orien_mat=None, face_scaling=None):
+    """Exports what the fused preprocess computes for the binding (no autograd): world means3D (P,3), opacities (P,1),
+    scales (P,3), cov3D (P,6).  Same device code as the fused forward -> bit-identical values."""
+    device = _xyz.device
+    P = _xyz.shape[0]
+    mod = raster_settings_or_modifier.scale_modifier if isinstance(raster_settings_or_modifier, tuple) \
+        else float(raster_settings_or_modifier)
+    a = N.ForwardArgs()
+    a.abi_version, a.input_mode, a.P, a.scale_modifier = N.ABI_VERSION, N.INPUT_BOUND_RAW, P, mod
+    keep = [_f32c(_xyz.detach(), "_xyz", device), _f32c(_rotation.detach(), "_rotation", device),
+            _f32c(_scaling.detach(), "_scaling", device), _f32c(_opacity.detach(), "_opacity", device)]
+    a.means3D, a.rotations, a.scales, a.opacities = (t.data_ptr() for t in keep)
+    if binding is not None:
+        keep += [binding.to(torch.int32).contiguous(), _f32c(face_center.detach(), "face_center", device),
+                 _f32c(face_orien_mat.detach(), "face_orien_mat", device),
+                 _f32c(face_scaling.detach(), "face_scaling", device)]
+        a.binding, a.face_center, a.face_orien_mat, a.face_scaling = (t.data_ptr() for t in keep[4:])
+        a.num_faces = keep[5].shape[0]
+    e = lambda *s: torch.empty(s, dtype=torch.float32, device=device)  # noqa: E731
+    means3D, opac, scales, cov = e(P, 3), e(P, 1), e(P, 3), e(P, 6)
+    with torch.cuda.device(device):
+        stream = torch.cuda.current_stream(device).cuda_stream
+        N.check(N.lib().gab200_bind_activate(C.byref(a), means3D.data_ptr(), opac.data_ptr(), scales.data_ptr(),
+                                             cov.data_ptr(), C.c_void_p(stream)), "gab200_bind_activate")
+    return means3D, opac, scales, cov

@@ -119,7 +119,7 @@ def head_mesh(n_lat=52, n_lon=98, seed=0):
     """Closed ellipsoidal stand-in for the FLAME head: 2*n_lon*(n_lat-1) = 9,996 + jitter faces ~ FLAME's 10,144.
     Returns verts (V,3) float32 centred at the origin and faces (F,3) int64."""
     g = np.random.default_rng(seed)
-    rx, ry, rz = 0.095, 0.14, 0.11
+    rx, ry, rz = 0.105, 0.16, 0.11
     verts = [(0.0, ry, 0.0)]
     for i in range(1, n_lat):
         th = math.pi * i / n_lat
@@ -152,11 +152,14 @@ def pose_mesh(verts: torch.Tensor, timestep: int):
     yaw, pitch = 0.15 * math.sin(0.37 * t), 0.08 * math.sin(0.23 * t + 1.0)
     Ry = torch.tensor([[math.cos(yaw), 0, math.sin(yaw)], [0, 1, 0], [-math.sin(yaw), 0, math.cos(yaw)]])
     Rx = torch.tensor([[1, 0, 0], [0, math.cos(pitch), -math.sin(pitch)], [0, math.sin(pitch), math.cos(pitch)]])
-    v = verts @ (Ry @ Rx).T.to(verts.dtype)
+    v = verts @ (Ry @ Rx).T.to(verts)
     jaw = torch.clamp((-v[:, 1] - 0.04) / 0.1, 0, 1) * (0.01 * (1 + math.sin(0.5 * t)))
     v = v.clone()
     v[:, 1] -= jaw
     return v
+
+
+SIZE0, SIZE_SIG = 0.19, 0.85
 
 
 def avatar_splats(P=100_000, n_faces=10_144, seed=0, sh_degree=3, scale_gain=1.0) -> Dict[str, torch.Tensor]:
@@ -173,12 +176,15 @@ def avatar_splats(P=100_000, n_faces=10_144, seed=0, sh_degree=3, scale_gain=1.0
     if P >= n_faces:
         binding[:n_faces] = torch.arange(n_faces, dtype=torch.int32)
     xyz = torch.randn(P, 3, generator=g) * torch.tensor([0.6, 0.6, 0.25])  # local (face) units
-    scaling = math.log(0.33 * scale_gain) + 0.9 * torch.randn(P, 3, generator=g)
+    # splat size: clipped log-normal body (radius quantiles of media/306: median 13 px, p90 43, p99 79, max 116 @1080p)
+    size = torch.clamp(torch.randn(P, 1, generator=g), -2.5, 1.9)
+    jitter = torch.clamp(torch.randn(P, 3, generator=g), -2.0, 2.0)
+    scaling = math.log(SIZE0 * scale_gain) + SIZE_SIG * size + 0.35 * jitter
     scaling[:, 2] -= 0.7  # flattened along the face normal
     degenerate = torch.rand(P, generator=g) < 0.003
     scaling[degenerate] = -40.0  # exp -> ~4e-18: the radius-0 / tiny path
     rotation = torch.randn(P, 4, generator=g) * (0.5 + 2.0 * torch.rand(P, 1, generator=g))  # unnormalised raw
-    opacity = 0.3 + 3.2 * torch.randn(P, 1, generator=g)
+    opacity = -0.4 + 3.0 * torch.randn(P, 1, generator=g)
     dead = torch.rand(P, generator=g) < 0.05
     opacity[dead] = -7.0  # sigmoid < 1/255: can never contribute, must keep radii>0
     f_dc = 0.8 * torch.randn(P, 1, 3, generator=g)

@@ -1,0 +1,181 @@
+/*
+ * gab200_rasterizer.h -- C ABI of the B200-native differentiable Gaussian-splat rasterizer with fused
+ * FLAME mesh binding (libgaussianavatars_b200.so).
+ *
+ * This is the drop-in boundary for the one native operator GaussianAvatars calls on its hot path:
+ *   reference call site ........ gaussian_renderer/__init__.py:15,37-52,86-94
+ *   reference native module .... diff_gaussian_rasterization._C (submodule graphdeco-inria/diff-gaussian-rasterization
+ *                                @59f5f77, ABSENT from /root/reference; its pybind surface is
+ *                                rasterize_gaussians / rasterize_gaussians_backward / mark_visible)
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - Every pointer is a DEVICE pointer owned by the caller unless stated otherwise; fp32 unless stated.
+ *   - Matrices are the row-major flatten of the (4,4) tensors GaussianAvatars builds
+ *     (world_view_transform = W2C^T, full_proj_transform = (P W2C)^T; scene/cameras.py:44-46).
+ *   - No hidden global state; thread-safe per stream; no exceptions cross the ABI: functions return
+ *     >= 0 on success and a negative gab200_status on failure (gab200_status_string() explains it).
+ *   - Scratch memory is obtained through caller-supplied allocation callbacks, mirroring the reference
+ *     module's three resizable byte buffers (geometry / binning / image).  The callbacks
+ *     are invoked on the calling host thread, must return device memory aligned to 256 B that stays valid
+ *     until the matching gab200_backward() has run (or is never called).
+ */
+#ifndef GAB200_RASTERIZER_H
+#define GAB200_RASTERIZER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GAB200_ABI_VERSION 1
+
+typedef enum gab200_status {
+  GAB200_OK = 0,
+  GAB200_ERR_INVALID_ARGUMENT = -1, /* bad shape / missing pointer / inconsistent option        */
+  GAB200_ERR_CUDA = -2,             /* a CUDA runtime call or kernel failed (see cudaGetLastError) */
+  GAB200_ERR_ALLOC = -3,            /* an allocation callback returned NULL                       */
+  GAB200_ERR_ARCH = -4,             /* device is not sm_100 class                                 */
+  GAB200_ERR_OVERFLOW = -5          /* more than 2^32-1 (splat,tile) instances                    */
+} gab200_status;
+
+/* Input interpretation. */
+typedef enum gab200_input_mode {
+  /* Reference surface: means3D world-space, scales already exp()-activated, rotations unit wxyz (used as given),
+   * opacities already sigmoid()-activated -- exactly what render() passes today
+   * (gaussian_renderer/__init__.py:54-94 <- scene/gaussian_model.py:113-160). */
+  GAB200_INPUT_ACTIVATED = 0,
+  /* Fused surface: the RAW parameters of GaussianModel (_xyz local, _scaling log, _rotation unnormalised,
+   * _opacity logit, _features_dc/_features_rest) plus the per-face frame; the binding transform of
+   * scene/gaussian_model.py:113-160 runs inside the preprocess kernel.  binding == NULL means identity frame. */
+  GAB200_INPUT_BOUND_RAW = 1
+} gab200_input_mode;
+
+typedef void* (*gab200_alloc_fn)(void* user, size_t bytes);
+
+/* Everything one frame's forward needs.  Replaces the argument list of
+ * diff_gaussian_rasterization._C.rasterize_gaussians. */
+typedef struct gab200_forward_args {
+  uint32_t abi_version;    /* = GAB200_ABI_VERSION */
+  int32_t input_mode;      /* gab200_input_mode */
+  int32_t P;               /* number of splats */
+  int32_t sh_degree;       /* active SH degree D (0..3) */
+  int32_t sh_coeffs;       /* M: coefficients stored per splat (1,4,9,16); 0 with colors_precomp */
+  int32_t image_width, image_height;
+  float tanfovx, tanfovy, scale_modifier;
+  int32_t prefiltered;     /* accepted for signature parity; the near-plane cull is always applied */
+  int32_t debug;           /* 1: synchronise + check after every stage (reference `debug=` flag) */
+  int32_t need_backward;   /* 0: inference -- per-pixel state for backward is not written */
+  int32_t exact_binning;   /* 1: emit the reference's full 3-sigma bounding-square instance list;
+                              0: additionally drop (splat,tile) pairs that provably contribute nothing
+                                 (alpha < 1/255 over the whole tile): image/gradients unchanged */
+
+  /* camera block */
+  const float* bg;         /* [3] */
+  const float* viewmatrix; /* [16] */
+  const float* projmatrix; /* [16] */
+  const float* campos;     /* [3] */
+
+  /* splat attributes (meaning depends on input_mode) */
+  const float* means3D;        /* [P,3]  world xyz | raw _xyz (face-local) */
+  const float* opacities;      /* [P]    sigmoid-ed | raw logit */
+  const float* scales;         /* [P,3]  exp-ed | raw log;            NULL iff cov3D_precomp */
+  const float* rotations;      /* [P,4]  wxyz unit | raw unnormalised; NULL iff cov3D_precomp */
+  const float* cov3D_precomp;  /* [P,6]  xx,xy,xz,yy,yz,zz; ACTIVATED mode only, else NULL */
+  const float* shs;            /* [P,M,3] ACTIVATED mode: concatenated SH; NULL with colors_precomp */
+  const float* sh_dc;          /* [P,1,3]   BOUND_RAW mode: _features_dc   (no torch.cat needed) */
+  const float* sh_rest;        /* [P,M-1,3] BOUND_RAW mode: _features_rest (may be NULL when M==1) */
+  const float* colors_precomp; /* [P,3]  overrides SH when non-NULL */
+
+  /* mesh binding (BOUND_RAW mode; scene/flame_gaussian_model.py:137-147) */
+  const int32_t* binding;        /* [P] face index per splat, or NULL (identity frame) */
+  int32_t num_faces;             /* F */
+  const float* face_center;      /* [F,3] */
+  const float* face_orien_mat;   /* [F,3,3] row-major, columns a0 a1 a2 */
+  const float* face_scaling;     /* [F] */
+
+  /* outputs */
+  float* out_color;   /* [3,H,W] */
+  int32_t* radii;     /* [P] */
+
+  /* scratch (the reference's geomBuffer / binningBuffer / imgBuffer) */
+  gab200_alloc_fn alloc_geom, alloc_binning, alloc_image;
+  void* alloc_user;
+} gab200_forward_args;
+
+/* Host-side handle to the state a forward leaves behind for its backward (what the reference keeps as
+ * num_rendered + the three byte buffers in the autograd ctx). Plain data; copy freely. */
+typedef struct gab200_frame_state {
+  int64_t num_rendered;       /* N: (splat,tile) instances sorted and blended */
+  int64_t num_candidates;     /* instances of the reference's bounding-square list (== N when exact_binning) */
+  void* geom_buffer;
+  void* binning_buffer;
+  void* image_buffer;
+  size_t geom_bytes, binning_bytes, image_bytes;
+  int32_t sorted_selector;    /* which half of the sort double-buffer holds the sorted stream */
+  int32_t sort_bits;          /* radix-sort key width used: 32 + bits(tile id) */
+} gab200_frame_state;
+
+/* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
+ * performs ONE host<->device synchronisation on that stream to size the binning buffer (as the reference does). */
+int64_t gab200_forward(const gab200_forward_args* args, gab200_frame_state* state_out, void* stream);
+
+/* Gradients.  Replaces rasterize_gaussians_backward.  All outputs are written in full
+ * (zeros where a splat received no gradient); NULL outputs are skipped where noted.
+ * ACTIVATED mode: dL_dmeans3D [P,3], dL_dmeans2D [P,3] (x,y in NDC units, z = 0), dL_dopacity [P],
+ *   dL_dcolors [P,3] (also the colors_precomp gradient), dL_dshs [P,M,3] | NULL, dL_dscales [P,3] | NULL,
+ *   dL_drotations [P,4] | NULL, dL_dcov3D [P,6].
+ * BOUND_RAW mode: same pointers are gradients w.r.t. the RAW parameters (_xyz, logit, log-scale, raw quaternion);
+ *   dL_dsh_dc [P,1,3], dL_dsh_rest [P,M-1,3]; plus the face-frame gradients dL_dface_center [F,3],
+ *   dL_dface_orien_mat [F,3,3], dL_dface_scaling [F] (accumulated; caller zero-initialises NOTHING -- the library does).
+ */
+typedef struct gab200_backward_args {
+  uint32_t abi_version;
+  const gab200_forward_args* fwd;   /* the same inputs the forward saw */
+  const gab200_frame_state* state;
+  const float* dL_dout_color;       /* [3,H,W] */
+  float* dL_dmeans3D;
+  float* dL_dmeans2D;
+  float* dL_dopacity;
+  float* dL_dcolors;
+  float* dL_dshs;
+  float* dL_dsh_dc;
+  float* dL_dsh_rest;
+  float* dL_dscales;
+  float* dL_drotations;
+  float* dL_dcov3D;
+  float* dL_dface_center;
+  float* dL_dface_orien_mat;
+  float* dL_dface_scaling;
+} gab200_backward_args;
+
+int32_t gab200_backward(const gab200_backward_args* args, void* stream);
+
+/* Frustum test only.  Replaces diff_gaussian_rasterization._C.mark_visible (GaussianRasterizer.markVisible). */
+int32_t gab200_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                            uint8_t* present /* [P] 0/1 */, void* stream);
+
+/* Runs ONLY the binding + activation part of the fused preprocess (scene/gaussian_model.py:113-160) and exports
+ * world-space means3D [P,3], opacities [P], scales [P,3] (exp * face scale) and cov3D [P,6] (with scale_modifier).
+ * Any output may be NULL.  Same device code as the fused forward -> bit-identical values (parity tests, and the
+ * callers that still need pc.get_xyz, e.g. convert_SHs_python). */
+int32_t gab200_bind_activate(const gab200_forward_args* args, float* means3D, float* opacities, float* scales,
+                             float* cov3D, void* stream);
+
+/* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
+ * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */
+int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,
+                              uint32_t* values, uint32_t* ranges, void* stream);
+
+/* Number of kernels launched by this library on the calling process so far (bench.py's gpu_launches claim). */
+int64_t gab200_launch_count(void);
+
+const char* gab200_status_string(int32_t status);
+uint32_t gab200_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GAB200_RASTERIZER_H */
