@@ -1,0 +1,419 @@
+#!/usr/bin/env python
+"""bench.py -- rasterizer forward+backward frames/s at BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (config.workload): BASELINE.json configs[1] -- ~100k mesh-bound splats, 1920x1080, SH degree 3, fused
+binding + rasterizer forward + backward, one camera per step per GPU.  media/306 cannot travel to the GPU box, so the
+splats are the seeded synthetic avatar of gaussianavatars_b200/synthetic.py, calibrated against media/306 through
+the oracle (DESIGN.md "Workload calibration").
+
+One "step" = one frame: mesh-frame update, fused forward, backward (+ for N>1 one NCCL all-reduce of the flat 59-float
+per-splat gradient buffer; frames shard by camera, "scaling": "weak").
+  value  : frames/s, all inputs resident in HBM (camera block, mesh, dL/dimage), L2 flushed between steps,
+           timed per step with CUDA events on the launching stream, max over ranks.
+  e2e    : the same metric through the public `render()` with HOST inputs: every step uploads the camera block and
+           the uint8 ground-truth image from pinned memory, computes an L1 loss, runs backward and reads the loss
+           scalar back (the data flow of the reference training step, train.py:113-170).
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+P_SPLATS = 100_000
+WIDTH, HEIGHT = 1920, 1080
+SH_DEGREE = 3
+N_CAMERAS = 16  # distinct orbit views cycled through
+METRIC = "rasterizer fwd+bwd frames/sec @100k splats 1080p"
+WORKLOAD = "avatar-100k-splats-1920x1080-sh3-fused-binding-fwd+bwd (BASELINE configs[1], synthetic media/306 stand-in)"
+
+
+class Pipe:
+    debug = False
+    compute_cov3D_python = False
+    convert_SHs_python = False
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=60)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exact-binning", action="store_true", help="emit the reference's full instance list")
+    return ap.parse_args()
+
+
+def make_cameras(n):
+    from gaussianavatars_b200 import synthetic as syn
+
+    cams = []
+    for i in range(n):
+        az = -60.0 + 120.0 * (i + 0.5) / n  # +-60 degree arc
+        c = syn.orbit_camera(WIDTH, HEIGHT, r=1.0, fovy_deg=20.0, azimuth_deg=az, elevation_deg=5.0 * math.sin(i))
+        c.timestep = i
+        cams.append(c)
+    return cams
+
+
+def algorithmic_bytes(P, N, W, H, F):
+    """SURVEY.md 8(d) per-unit figures (SH3, fused, training mode) -- compulsory traffic per frame, by stage."""
+    c_in = 240
+    return {
+        "preprocess": P * c_in + P * (48 + 28),
+        "scan": P * 8,
+        "emit_keys": P * 48 + N * 12,
+        "sort": N * 24,
+        "tile_ranges": N * 8,
+        "blend_fwd": N * 40 + H * W * (12 + 8),
+        "blend_bwd": H * W * 20 + N * 40 + P * 44,
+        "preprocess_bwd": P * 44 + P * (c_in + 76) + P * 236 + F * 52,
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks sampler (recipe: B200_PROFILING.md "clocks DURING the timed region")
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on the host cores (bench.py's cpu_baseline and --impl reference)
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_frames(params, verts, faces, cams, frames, threads=None):
+    """Runs `frames` full fwd+bwd frames of the same workload through the CPU oracle (eager torch binding getters +
+    C rasterizer, OpenMP over all host cores).  Returns (seconds per frame list, binding seconds per frame list)."""
+    import numpy as np
+
+    from oracle import binding as ob
+    from oracle import rasterizer as orc
+
+    if threads:
+        torch.set_num_threads(threads)
+    bg = np.ones(3, np.float32)
+    gout = torch.randn(3, HEIGHT, WIDTH, generator=torch.Generator().manual_seed(1)).numpy()
+    from gaussianavatars_b200 import synthetic as syn
+
+    times, bind_times = [], []
+    for i in range(frames):
+        cam = cams[i % len(cams)]
+        t0 = time.perf_counter()
+        v = syn.pose_mesh(verts, cam.timestep)
+        fr = ob.update_mesh_properties(v, faces)
+        b = params["binding"].long()
+        xyz = ob.get_xyz(params["_xyz"], b, fr["face_center"], fr["face_orien_mat"], fr["face_scaling"])
+        sc = ob.get_scaling(params["_scaling"], b, fr["face_scaling"])
+        ro = ob.get_rotation(params["_rotation"], b, fr["face_orien_quat"])
+        op = ob.get_opacity(params["_opacity"])
+        sh = ob.get_features(params["_features_dc"], params["_features_rest"]).contiguous()
+        t1 = time.perf_counter()
+        kw = dict(shs=sh.numpy(), sh_degree=SH_DEGREE, scales=sc.numpy(), rotations=ro.numpy())
+        st = orc.forward(xyz.numpy(), op.numpy(), cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(),
+                         cam.camera_center.numpy(), WIDTH, HEIGHT, cam.tanfovx, cam.tanfovy, bg, **kw)
+        orc.backward(st, gout, xyz.numpy(), cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(),
+                     cam.camera_center.numpy(), cam.tanfovx, cam.tanfovy, bg, **kw)
+        t2 = time.perf_counter()
+        times.append(t2 - t0)
+        bind_times.append(t1 - t0)
+    return times, bind_times
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  The rasterizer submodule is absent from
+    /root/reference (unbuildable), so this is the oracle PORT (cpu_baseline.kind = "port") on all host cores."""
+    if rank != 0:
+        return
+    from gaussianavatars_b200 import synthetic as syn
+
+    verts, faces = syn.head_mesh()
+    params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
+    cams = make_cameras(N_CAMERAS)
+    cores = os.cpu_count() or 1
+    # bounded sample: one frame per step, steps capped so the whole run stays within ~2 minutes
+    steps = max(1, min(args.steps, 12))
+    warm = max(1, min(args.warmup, 2))
+    cpu_frames(params, verts, faces, cams, warm)
+    t, _ = cpu_frames(params, verts, faces, cams, steps)
+    sec = sum(t) / len(t)
+    fps = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "splats": P_SPLATS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                         "sample": f"{steps} full frames (binding getters + rasterizer fwd+bwd), OpenMP x{cores}"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+
+    from gaussianavatars_b200 import _native as N
+    from gaussianavatars_b200 import dist as gdist
+    from gaussianavatars_b200 import rasterizer as R
+    from gaussianavatars_b200 import synthetic as syn
+    from gaussianavatars_b200.model import MeshBoundGaussians
+    from gaussianavatars_b200.renderer import render
+
+    assert torch.cuda.is_available(), "bench.py (native arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    N.lib()
+    R.set_exact_binning(args.exact_binning)
+    R.keep_last_state(True)
+
+    verts, faces = syn.head_mesh()
+    params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
+    pc = MeshBoundGaussians(params, SH_DEGREE, verts, faces, pose_fn=syn.pose_mesh, device=dev, requires_grad=True)
+    cams_host = make_cameras(N_CAMERAS)
+    my_cams = [cams_host[i] for i in gdist.shard_frames(N_CAMERAS, rank, world)] or cams_host
+    cams_dev = [c.to(dev) for c in my_cams]
+    bg = torch.ones(3, device=dev)
+    gout = torch.randn(3, HEIGHT, WIDTH, generator=torch.Generator().manual_seed(1)).to(dev) / (3 * HEIGHT * WIDTH)
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
+
+    def zero_grads():
+        for p in pc.parameters():
+            p.grad = None
+
+    def step_resident(i):
+        """HBM-resident step: everything already on the device."""
+        cam = cams_dev[i % len(cams_dev)]
+        zero_grads()
+        pc.select_mesh_by_timestep(cam.timestep)
+        out = render(cam, pc, Pipe, bg)
+        out["render"].backward(gout)
+        gdist.allreduce_splat_grads(pc)
+        return out
+
+    # e2e: host-resident inputs
+    gt_host = [torch.randint(0, 256, (3, HEIGHT, WIDTH), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    cam_host_blocks = []
+    for c in my_cams:
+        blk = torch.cat((c.world_view_transform.reshape(-1), c.full_proj_transform.reshape(-1), c.camera_center)).pin_memory()
+        cam_host_blocks.append(blk)
+    h2d_bytes = gt_host[0].numel() + cam_host_blocks[0].numel() * 4
+    copy_stream = torch.cuda.Stream(device=dev)
+
+    def step_e2e(i):
+        cam = my_cams[i % len(my_cams)]
+        zero_grads()
+        with torch.cuda.stream(copy_stream):
+            gt_u8 = gt_host[i % 2].to(dev, non_blocking=True)
+        blk = cam_host_blocks[i % len(my_cams)].to(dev, non_blocking=True)
+        dcam = syn.SyntheticCamera(cam.image_width, cam.image_height, cam.FoVx, cam.FoVy, blk[0:16].view(4, 4),
+                                   blk[16:32].view(4, 4), blk[32:35], cam.timestep)
+        pc.select_mesh_by_timestep(cam.timestep)
+        out = render(dcam, pc, Pipe, bg)
+        torch.cuda.current_stream(dev).wait_stream(copy_stream)
+        gt_u8.record_stream(torch.cuda.current_stream(dev))
+        gt = gt_u8.to(torch.float32).mul_(1.0 / 255.0)
+        loss = (out["render"] - gt).abs().mean()
+        loss.backward()
+        gdist.allreduce_splat_grads(pc)
+        return float(loss.item())  # D2H read of the step's result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up -------------------------------------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+    _, _, _, n_inst = R.export_last_binning()
+
+    # ---- timed region: HBM-resident, L2 flushed between steps, per-step CUDA events -------------------------
+    K = args.steps
+    N.stage_timing(True)
+    N.stage_times(reset=True)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    launches0 = N.launch_count()
+    barrier()
+    with ClockSampler(local_rank) as clk:
+        wall0 = time.perf_counter()
+        for i in range(K):
+            flush_buf.fill_(i & 0xFF)  # L2 flush (outside the step's event pair)
+            starts[i].record()
+            step_resident(i)
+            ends[i].record()
+        barrier()
+        wall1 = time.perf_counter()
+    launches = N.launch_count() - launches0
+    stage = N.stage_times(reset=True)
+    N.stage_timing(False)
+    ms_steps = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    ms_total = sum(ms_steps)
+
+    # ---- warm-L2 variant (no flush), whole-loop events: what a training loop actually sees -------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(K):
+        step_resident(i)
+    e1.record()
+    barrier()
+    ms_warm = e0.elapsed_time(e1)
+
+    # ---- e2e -------------------------------------------------------------------------------------------------
+    for i in range(3):
+        step_e2e(i)
+    barrier()
+    e0.record()
+    for i in range(K):
+        step_e2e(i)
+    e1.record()
+    barrier()
+    ms_e2e = e0.elapsed_time(e1)
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ms_total, ms_warm, ms_e2e = max_over_ranks(ms_total), max_over_ranks(ms_warm), max_over_ranks(ms_e2e)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    fps = world * K / (ms_total / 1e3)
+    F = faces.shape[0]
+    alg = algorithmic_bytes(P_SPLATS, n_inst, WIDTH, HEIGHT, F)
+    stage_ms = {k: (v[0] / max(v[1], 1)) for k, v in stage.items()}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
+        traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    frame_alg = sum(alg.values())
+    line = {
+        "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "splats": P_SPLATS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
+                   "faces": F, "instances_per_frame": int(n_inst), "binning": "exact" if args.exact_binning else "culled",
+                   "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded dp{world}",
+                   "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
+        "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},
+        "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
+                     "peak_source": "measured" if peaks else "fallback", "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom],
+                     "avg_launch_ms": stage_ms[dom],
+                     "frame": {"algorithmic_bytes": frame_alg,
+                               "achieved_gbs": frame_alg / ((ms_total / K) * 1e-3) / 1e9,
+                               "frac": frame_alg / ((ms_total / K) * 1e-3) / 1e9 / peak}},
+        "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "wall_s_timed_region": wall1 - wall0,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        cpu_params = {k: v for k, v in params.items()}
+        cpu_frames(cpu_params, verts, faces, cams_host, 1)
+        frames = 6
+        t, tb = cpu_frames(cpu_params, verts, faces, cams_host, frames)
+        sec = sum(t) / len(t)
+        line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"{frames} full frames of the same workload (eager torch binding getters + "
+                                          f"C oracle rasterizer fwd+bwd, OpenMP x{cores})",
+                                "binding_ms_per_frame": 1e3 * sum(tb) / len(tb)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

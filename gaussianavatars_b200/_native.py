@@ -59,7 +59,8 @@ class BackwardArgs(C.Structure):
 
 
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
-                    "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version")
+                    "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
+                    "gab200_stage_timing_enable", "gab200_stage_times")
 
 _lib = None
 _lock = threading.Lock()
@@ -104,6 +105,10 @@ def lib():
         L.gab200_status_string.restype = C.c_char_p
         L.gab200_status_string.argtypes = [C.c_int32]
         L.gab200_abi_version.restype = C.c_uint32
+        L.gab200_stage_timing_enable.restype = None
+        L.gab200_stage_timing_enable.argtypes = [C.c_int32]
+        L.gab200_stage_times.restype = C.c_int32
+        L.gab200_stage_times.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32]
         if L.gab200_abi_version() != ABI_VERSION:
             raise NativeLibraryError("ABI version mismatch between _native.py and the shared library")
         _lib = L
@@ -115,6 +120,21 @@ def check(status: int, what: str):
         msg = lib().gab200_status_string(int(status)).decode()
         raise RuntimeError(f"{what} failed: {msg} (status {status})")
     return status
+
+
+STAGES = ("preprocess", "scan", "emit_keys", "sort", "tile_ranges", "blend_fwd", "blend_bwd", "preprocess_bwd")
+
+
+def stage_timing(enable: bool):
+    lib().gab200_stage_timing_enable(int(enable))
+
+
+def stage_times(reset: bool = True):
+    """{stage: (total_ms, launches)} since the last reset (synchronises the pending events)."""
+    ms = (C.c_double * len(STAGES))()
+    n = (C.c_int64 * len(STAGES))()
+    check(lib().gab200_stage_times(ms, n, int(reset)), "gab200_stage_times")
+    return {s: (ms[i], n[i]) for i, s in enumerate(STAGES)}
 
 
 def launch_count() -> int:

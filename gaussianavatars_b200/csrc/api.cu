@@ -4,6 +4,8 @@
 #include <atomic>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.cuh"
@@ -72,6 +74,39 @@ static ImageView carve_image(void* base, int W, int H, bool need_backward) {
   return v;
 }
 
+// ---- opt-in stage timing -------------------------------------------------------------------------------
+struct StageTimer {
+  std::atomic<int> enabled{0};
+  std::mutex mu;
+  struct Pending { int stage; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
+  double total_ms[GAB200_NUM_STAGES] = {0};
+  int64_t launches[GAB200_NUM_STAGES] = {0};
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+static StageTimer g_timer;
+struct StageScope {
+  int stage; cudaStream_t stream; cudaEvent_t a{}, b{}; bool on;
+  StageScope(int st, cudaStream_t s) : stage(st), stream(s), on(g_timer.enabled.load() != 0) {
+    if (on) {
+      std::lock_guard<std::mutex> l(g_timer.mu);
+      a = g_timer.get(); b = g_timer.get();
+      cudaEventRecord(a, stream);
+    }
+  }
+  ~StageScope() {
+    if (on) {
+      cudaEventRecord(b, stream);
+      std::lock_guard<std::mutex> l(g_timer.mu);
+      g_timer.pending.push_back({stage, a, b});
+    }
+  }
+};
+
 static int check_arch() {
   static std::atomic<int> cached{0};  // 0 unknown, 1 ok, -1 bad
   int c = cached.load();
@@ -132,6 +167,28 @@ using namespace gab;
 extern "C" {
 
 uint32_t gab200_abi_version(void) { return GAB200_ABI_VERSION; }
+
+void gab200_stage_timing_enable(int32_t enable) { g_timer.enabled.store(enable ? 1 : 0); }
+
+int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[GAB200_NUM_STAGES], int32_t reset) {
+  std::lock_guard<std::mutex> l(g_timer.mu);
+  for (auto& p : g_timer.pending) {
+    if (cudaEventSynchronize(p.b) != cudaSuccess) return GAB200_ERR_CUDA;
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.a, p.b) != cudaSuccess) return GAB200_ERR_CUDA;
+    g_timer.total_ms[p.stage] += ms;
+    g_timer.launches[p.stage] += 1;
+    g_timer.pool.push_back(p.a);
+    g_timer.pool.push_back(p.b);
+  }
+  g_timer.pending.clear();
+  for (int i = 0; i < GAB200_NUM_STAGES; i++) {
+    if (total_ms) total_ms[i] = g_timer.total_ms[i];
+    if (launches) launches[i] = g_timer.launches[i];
+    if (reset) { g_timer.total_ms[i] = 0; g_timer.launches[i] = 0; }
+  }
+  return GAB200_OK;
+}
 int64_t gab200_launch_count(void) { return g_launches.load(); }
 
 const char* gab200_status_string(int32_t s) {
@@ -171,9 +228,15 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
 
   int64_t N = 0;
   if (P > 0) {
-    launch_preprocess(*a, g.rec, g.tiles_touched, nb ? g.clamped : nullptr, stream);
+    {
+      StageScope sc(GAB200_STAGE_PREPROCESS, stream);
+      launch_preprocess(*a, g.rec, g.tiles_touched, nb ? g.clamped : nullptr, stream);
+    }
     GAB_STAGE_CHECK(dbg, stream);
-    GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.offsets, P, stream));
+    {
+      StageScope sc(GAB200_STAGE_SCAN, stream);
+      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.offsets, P, stream));
+    }
     GAB_STAGE_CHECK(dbg, stream);
     uint32_t n_host = 0;
     GAB_CUDA(cudaMemcpyAsync(&n_host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
@@ -192,17 +255,29 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
   int selector = 0;
   if (N > 0) {
-    launch_emit_keys(P, gx, gy, g.rec, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+    {
+      StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
+      launch_emit_keys(P, gx, gy, g.rec, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+    }
     GAB_STAGE_CHECK(dbg, stream);
-    GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], N,
-                      st->sort_bits, &selector, stream));
+    {
+      StageScope sc(GAB200_STAGE_SORT, stream);
+      GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], N,
+                        st->sort_bits, &selector, stream));
+    }
     GAB_STAGE_CHECK(dbg, stream);
-    launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
+    {
+      StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+      launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
+    }
     GAB_STAGE_CHECK(dbg, stream);
   }
   st->sorted_selector = selector;
-  launch_blend_forward(W, H, iv.ranges, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
-                       stream);
+  {
+    StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
+    launch_blend_forward(W, H, iv.ranges, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
+                         stream);
+  }
   GAB_STAGE_CHECK(dbg, stream);
   return N;
 }
@@ -239,11 +314,15 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
       GAB_CUDA(cudaMemsetAsync(b->dL_dsh_rest, 0, sizeof(float) * 3 * (size_t)(a->sh_coeffs - 1) * P, stream));
   }
   if (st->num_rendered > 0) {
+    StageScope sc(GAB200_STAGE_BLEND_BWD, stream);
     launch_blend_backward(W, H, iv.ranges, bv.vals[st->sorted_selector], g.rec, a->bg, iv.final_T, iv.n_contrib,
                           b->dL_dout_color, g.g2d, stream);
-    GAB_STAGE_CHECK(dbg, stream);
   }
-  launch_preprocess_backward(*b, g.rec, g.clamped, g.g2d, stream);
+  GAB_STAGE_CHECK(dbg, stream);
+  {
+    StageScope sc(GAB200_STAGE_PREPROCESS_BWD, stream);
+    launch_preprocess_backward(*b, g.rec, g.clamped, g.g2d, stream);
+  }
   GAB_STAGE_CHECK(dbg, stream);
   return GAB200_OK;
 }

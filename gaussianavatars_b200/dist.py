@@ -1,0 +1,69 @@
+"""Frame-sharded data parallelism: every rank holds the full splat model, renders its own cameras,
+and the per-splat parameter gradients are summed with ONE NCCL all-reduce over NVLink/NVSwitch.
+
+The reference has no multi-GPU code at all; this is the new capability north_star asks for.  No
+collective touches the data path of a frame: frames are independent given the parameters.  The fused backward
+already writes all six parameter gradients into one flat fp32 buffer (59 floats/splat at SH3 = 236 B/splat), which
+is the communication buffer itself -- no pack/unpack pass precedes the collective.
+"""
+from __future__ import annotations
+
+from typing import Iterable, List, Sequence
+
+import torch
+import torch.distributed as dist
+
+
+def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
+    """Camera indices rendered by `rank`: round-robin r, r+W, r+2W, ... (reference: one camera per step, train.py:113)."""
+    return list(range(rank, num_frames, world_size))
+
+
+def _flat_covers(flat: torch.Tensor, grads: Sequence[torch.Tensor]) -> bool:
+    if flat is None:
+        return False
+    lo, hi = flat.data_ptr(), flat.data_ptr() + flat.numel() * flat.element_size()
+    total = 0
+    for g in grads:
+        if g is None or not g.is_contiguous() or g.dtype != flat.dtype:
+            return False
+        if not (lo <= g.data_ptr() and g.data_ptr() + g.numel() * g.element_size() <= hi):
+            return False
+        total += g.numel()
+    return total == flat.numel()
+
+
+def allreduce_splat_grads(pc, params: Iterable[torch.Tensor] = None, group=None, average: bool = False) -> int:
+    """Sum (or average) the splat-parameter gradients over ranks.  Returns the number of collectives issued
+    (1 when the gradients still alias the fused backward's flat buffer, else one coalesced fallback)."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return 0
+    params = list(pc.parameters() if params is None else params)
+    grads = [p.grad for p in params]
+    flat = getattr(pc, "flat_grad", None)
+    world = dist.get_world_size(group)
+    if _flat_covers(flat, grads):
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat.div_(world)
+        return 1
+    live = [g for g in grads if g is not None]
+    buf = torch.cat([g.reshape(-1) for g in live])
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    if average:
+        buf.div_(world)
+    off = 0
+    for g in live:
+        g.copy_(buf[off:off + g.numel()].view_as(g))
+        off += g.numel()
+    return 1
+
+
+def allreduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=None):
+    """The three per-splat statistics the densifier consumes (scene/gaussian_model.py:517-519, train.py:197):
+    sum, sum, max."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)

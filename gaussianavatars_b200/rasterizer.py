@@ -238,8 +238,9 @@ class GaussianRasterizer(nn.Module):
 class _RasterizeBound(torch.autograd.Function):
     @staticmethod
     def forward(ctx, _xyz, means2D, _rotation, _scaling, _opacity, f_dc, f_rest, face_center, face_orien_mat,
-                face_scaling, binding, colors_precomp, raster_settings):
+                face_scaling, binding, colors_precomp, raster_settings, grad_sink=None):
         rs = raster_settings
+        ctx.grad_sink = grad_sink
         device = _xyz.device
         if device.type != "cuda":
             raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
@@ -319,12 +320,15 @@ class _RasterizeBound(torch.autograd.Function):
             stream = torch.cuda.current_stream(device).cuda_stream
             N.check(N.lib().gab200_backward(C.byref(b), C.c_void_p(stream)), "gab200_backward")
         ctx.holder = None
-        return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None)
+        if ctx.grad_sink is not None:  # dist.py: ONE all-reduce over this buffer instead of six
+            ctx.grad_sink.flat_grad = flat
+            ctx.grad_sink.flat_grad_views = (d_xyz, d_rot, d_scale, d_opac, d_dc, d_rest)
+        return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None, None)
 
 
 def rasterize_bound(raster_settings: GaussianRasterizationSettings, _xyz, _rotation, _scaling, _opacity,
                     features_dc, features_rest, binding=None, face_center=None, face_orien_mat=None,
-                    face_scaling=None, means2D=None, colors_precomp=None):
+                    face_scaling=None, means2D=None, colors_precomp=None, grad_sink=None):
     """Fused binding + rasterization.  Returns (color (3,H,W), radii (P,) int32).
 
     binding=None is the identity frame (a plain GaussianModel, scene/gaussian_model.py:115-116,127-128,142-143).
@@ -334,7 +338,8 @@ def rasterize_bound(raster_settings: GaussianRasterizationSettings, _xyz, _rotat
     if _opacity.ndim == 1:
         _opacity = _opacity[:, None]
     return _RasterizeBound.apply(_xyz, means2D, _rotation, _scaling, _opacity, features_dc, features_rest,
-                                 face_center, face_orien_mat, face_scaling, binding, colors_precomp, raster_settings)
+                                 face_center, face_orien_mat, face_scaling, binding, colors_precomp, raster_settings,
+                                 grad_sink)
 
 
 def bind_activate(raster_settings_or_modifier, _xyz, _rotation, _scaling, _opacity, binding=None, face_center=None,

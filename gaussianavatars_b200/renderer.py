@@ -61,7 +61,7 @@ def render_bound(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, ove
         fc, fR, fs = pc.face_center, pc.face_orien_mat, pc.face_scaling
     rendered_image, radii = rasterize_bound(rs, pc._xyz, pc._rotation, pc._scaling, pc._opacity, pc._features_dc,
                                             pc._features_rest, binding, fc, fR, fs, means2D=screenspace_points,
-                                            colors_precomp=override_color)
+                                            colors_precomp=override_color, grad_sink=pc)
     return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
             "radii": radii}
 

@@ -169,6 +169,23 @@ int32_t gab200_bind_activate(const gab200_forward_args* args, float* means3D, fl
 int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,
                               uint32_t* values, uint32_t* ranges, void* stream);
 
+/* Opt-in per-stage device timing (profiling aid used by bench.py's roofline line).  When enabled, forward/backward
+ * bracket every stage with cudaEvents on the launching stream.  gab200_stage_times() synchronises the pending
+ * events, adds them to per-stage totals and returns totals (milliseconds) and launch counts since the last reset. */
+enum {
+  GAB200_STAGE_PREPROCESS = 0,
+  GAB200_STAGE_SCAN = 1,
+  GAB200_STAGE_EMIT_KEYS = 2,
+  GAB200_STAGE_SORT = 3,
+  GAB200_STAGE_TILE_RANGES = 4,
+  GAB200_STAGE_BLEND_FWD = 5,
+  GAB200_STAGE_BLEND_BWD = 6,
+  GAB200_STAGE_PREPROCESS_BWD = 7,
+  GAB200_NUM_STAGES = 8
+};
+void gab200_stage_timing_enable(int32_t enable);
+int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[GAB200_NUM_STAGES], int32_t reset);
+
 /* Number of kernels launched by this library on the calling process so far (bench.py's gpu_launches claim). */
 int64_t gab200_launch_count(void);
 

@@ -14,11 +14,12 @@ cam = syn.orbit_camera(W, H)
 class Pipe: debug=False; compute_cov3D_python=False; convert_SHs_python=False
 bg = torch.ones(3, device=dev)
 gout = torch.randn(3, H, W, device=dev)
-for exact in (True, False):
+FAST = os.environ.get('FAST') == '1'
+for exact in ((False,) if FAST else (True, False)):
     R.set_exact_binning(exact); R.keep_last_state(True)
     pc = MeshBoundGaussians(params, 3, verts, faces, device=dev, requires_grad=True)
     pc.select_mesh_by_timestep(0)
-    for fused in (True, False):
+    for fused in ((True,) if FAST else (True, False)):
         def step(bw=True):
             out = render(cam, pc, Pipe, bg, fused=fused)
             if bw:
@@ -37,5 +38,11 @@ for exact in (True, False):
                 else:
                     with torch.no_grad(): step(False)
             ev[1].record(); torch.cuda.synchronize(); t1 = time.perf_counter()
+            if bw:
+                from gaussianavatars_b200 import _native as NN
+                NN.stage_timing(True); NN.stage_times(True)
+                for _ in range(10): step(True)
+                st_ = NN.stage_times(True); NN.stage_timing(False)
+                print("   stages us:", {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in st_.items()}, flush=True)
             print(f"exact={exact} fused={fused} bw={bw} N={n} vis={int((out['radii']>0).sum())} "
                   f"gpu {ev[0].elapsed_time(ev[1])/iters*1e3:.1f} us/frame wall {(t1-t0)/iters*1e6:.1f} us/frame", flush=True)
