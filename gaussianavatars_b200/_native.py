@@ -60,7 +60,8 @@ class BackwardArgs(C.Structure):
 
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
-                    "gab200_stage_timing_enable", "gab200_stage_times")
+                    "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
+                    "gab200_face_frame_backward")
 
 _lib = None
 _lock = threading.Lock()
@@ -102,6 +103,10 @@ def lib():
         L.gab200_export_binning.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
         L.gab200_launch_count.restype = C.c_int64
+        L.gab200_face_frame_forward.restype = C.c_int32
+        L.gab200_face_frame_forward.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 6
+        L.gab200_face_frame_backward.restype = C.c_int32
+        L.gab200_face_frame_backward.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 7
         L.gab200_status_string.restype = C.c_char_p
         L.gab200_status_string.argtypes = [C.c_int32]
         L.gab200_abi_version.restype = C.c_uint32

@@ -25,6 +25,7 @@ SOURCES = {
     "preprocess_bwd.cu": [],
     "binning.cu": [],
     "blend.cu": [],
+    "face_frame.cu": [],
 }
 
 

@@ -16,6 +16,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct GeomView {
   SplatRec* rec;
+  SplatAux* aux;
   uint32_t* tiles_touched;
   uint32_t* offsets;
   uint8_t* clamped;
@@ -28,6 +29,7 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   GeomView g;
   Carver c(base);
   g.rec = c.take<SplatRec>((size_t)P);
+  g.aux = c.take<SplatAux>((size_t)P);
   g.tiles_touched = c.take<uint32_t>((size_t)P);
   g.offsets = c.take<uint32_t>((size_t)P);
   g.clamped = c.take<uint8_t>((size_t)P);
@@ -40,11 +42,12 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
 struct BinView {
   uint64_t* keys[2];
   uint32_t* vals[2];
+  uint8_t* strip_mask;  // per sorted instance: which 16x2 pixel strips of its tile it contributed to (forward -> backward)
   void* sort_temp;
   size_t sort_temp_bytes;
   size_t bytes;
 };
-static BinView carve_binning(void* base, int64_t N, int sort_bits) {
+static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_backward) {
   BinView b;
   Carver c(base);
   const size_t n = (size_t)(N > 0 ? N : 1);
@@ -52,6 +55,7 @@ static BinView carve_binning(void* base, int64_t N, int sort_bits) {
   b.keys[1] = c.take<uint64_t>(n);
   b.vals[0] = c.take<uint32_t>(n);
   b.vals[1] = c.take<uint32_t>(n);
+  b.strip_mask = need_backward ? c.take<uint8_t>(n) : nullptr;
   b.sort_temp_bytes = sort_temp_bytes(N > 0 ? N : 1, sort_bits);
   b.sort_temp = c.take<char>(b.sort_temp_bytes);
   b.bytes = c.bytes();
@@ -59,6 +63,8 @@ static BinView carve_binning(void* base, int64_t N, int sort_bits) {
 }
 struct ImageView {
   uint2* ranges;
+  uint32_t* order;
+  uint32_t* order_info;
   float* final_T;
   uint32_t* n_contrib;
   size_t bytes;
@@ -68,6 +74,8 @@ static ImageView carve_image(void* base, int W, int H, bool need_backward) {
   Carver c(base);
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   v.ranges = c.take<uint2>((size_t)gx * gy);
+  v.order = c.take<uint32_t>((size_t)gx * gy);
+  v.order_info = c.take<uint32_t>(4);
   v.final_T = need_backward ? c.take<float>((size_t)W * H) : nullptr;
   v.n_contrib = need_backward ? c.take<uint32_t>((size_t)W * H) : nullptr;
   v.bytes = c.bytes();
@@ -230,7 +238,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (P > 0) {
     {
       StageScope sc(GAB200_STAGE_PREPROCESS, stream);
-      launch_preprocess(*a, g.rec, g.tiles_touched, nb ? g.clamped : nullptr, stream);
+      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
@@ -246,18 +254,19 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   st->num_rendered = N;
   st->num_candidates = N;
 
-  BinView bsz = carve_binning(nullptr, N, st->sort_bits);
+  BinView bsz = carve_binning(nullptr, N, st->sort_bits, nb);
   void* bin = a->alloc_binning(a->alloc_user, bsz.bytes);
   if (bin == nullptr) return GAB200_ERR_ALLOC;
-  BinView bv = carve_binning(bin, N, st->sort_bits);
+  BinView bv = carve_binning(bin, N, st->sort_bits, nb);
   st->binning_buffer = bin; st->binning_bytes = bv.bytes;
 
   GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+  if (bv.strip_mask != nullptr && N > 0) GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)N, stream));
   int selector = 0;
   if (N > 0) {
     {
       StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(P, gx, gy, g.rec, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
@@ -274,9 +283,13 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   }
   st->sorted_selector = selector;
   {
+    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+    launch_tile_order(gx * gy, iv.ranges, iv.order, iv.order_info, stream);
+  }
+  {
     StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
-    launch_blend_forward(W, H, iv.ranges, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
-                         stream);
+    launch_blend_forward(W, H, iv.ranges, iv.order, iv.order_info, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
+                         bv.strip_mask, stream);
   }
   GAB_STAGE_CHECK(dbg, stream);
   return N;
@@ -299,7 +312,7 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
   if (P == 0) return GAB200_OK;
   GeomView g = carve_geom(st->geom_buffer, P, true);
   ImageView iv = carve_image(st->image_buffer, W, H, true);
-  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits);
+  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, true);
 
   GAB_CUDA(cudaMemsetAsync(g.g2d, 0, sizeof(float) * (size_t)P * GAB_G2D_STRIDE, stream));
   if (bound && a->binding != nullptr) {
@@ -315,13 +328,13 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
   }
   if (st->num_rendered > 0) {
     StageScope sc(GAB200_STAGE_BLEND_BWD, stream);
-    launch_blend_backward(W, H, iv.ranges, bv.vals[st->sorted_selector], g.rec, a->bg, iv.final_T, iv.n_contrib,
-                          b->dL_dout_color, g.g2d, stream);
+    launch_blend_backward(W, H, iv.ranges, iv.order, iv.order_info, bv.vals[st->sorted_selector], g.rec, a->bg, iv.final_T, iv.n_contrib,
+                          b->dL_dout_color, bv.strip_mask, g.g2d, stream);
   }
   GAB_STAGE_CHECK(dbg, stream);
   {
     StageScope sc(GAB200_STAGE_PREPROCESS_BWD, stream);
-    launch_preprocess_backward(*b, g.rec, g.clamped, g.g2d, stream);
+    launch_preprocess_backward(*b, g.rec, g.aux, g.clamped, g.g2d, stream);
   }
   GAB_STAGE_CHECK(dbg, stream);
   return GAB200_OK;
@@ -348,6 +361,24 @@ int32_t gab200_bind_activate(const gab200_forward_args* a, float* means3D, float
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 
+int32_t gab200_face_frame_forward(int32_t F, int32_t V, const float* verts, const int32_t* faces, float* fc, float* fR,
+                                  float* fs, void* stream_) {
+  if (F < 0 || V < 0 || (F > 0 && (!verts || !faces || !fc || !fR || !fs))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  launch_face_frame_forward(F, verts, faces, fc, fR, fs, (cudaStream_t)stream_);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, const int32_t* faces, const float* g_fc,
+                                   const float* g_fR, const float* g_fs, float* g_verts, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (F < 0 || V < 0 || (V > 0 && !g_verts) || (F > 0 && (!verts || !faces))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(cudaMemsetAsync(g_verts, 0, sizeof(float) * 3 * (size_t)V, stream));
+  launch_face_frame_backward(F, verts, faces, g_fc, g_fR, g_fs, g_verts, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
 int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_state* st, uint64_t* keys,
                               uint32_t* values, uint32_t* ranges, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -355,7 +386,7 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
     return GAB200_ERR_INVALID_ARGUMENT;
   const int W = a->image_width, H = a->image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
-  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits);
+  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, a->need_backward != 0);
   ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
   const size_t N = (size_t)st->num_rendered;
   if (keys && N) GAB_CUDA(cudaMemcpyAsync(keys, bv.keys[st->sorted_selector], 8 * N, cudaMemcpyDeviceToDevice, stream));

@@ -1,17 +1,24 @@
 // blend.cu -- per-tile front-to-back alpha blend (forward) and reverse-walk gradient (backward) for sm_100a.
 // Replaces renderCUDA fwd/bwd of the reference module.
 //
-// B200-first mapping (NOT the reference's 1 thread = 1 pixel, 256-thread block):
-//   * one CTA per 16x16 tile with 256/K threads; every thread owns a COLUMN STRIP of K pixels.  The x-offset to a
-//     splat (dx) is then shared by the K pixels, so the exponent is 3 flops per pixel,
+// B200-first mapping (NOT the reference's 1 thread = 1 pixel, 256-thread block for every tile):
+//   * COLUMN STRIPS: a thread owns K vertically adjacent pixels of one column.  The x-offset to a splat (dx) is
+//     shared by the K pixels, so the exponent costs 3 flops per pixel,
 //         power(dy) = p0 + dy * (q + h * dy),   p0 = -A dx^2/2, q = -B dx, h = -C/2   (pre-scaled by log2 e -> ex2),
 //     and the shared-memory broadcast reads of the splat record are amortised K times.
+//   * HYBRID TILE SCHEDULE: the tiles are launched heaviest-first (tile_order_kernel).  A CTA takes either ONE heavy
+//     tile with many warps and few pixels per thread (short per-warp critical path for 2000-deep lists) or SEVERAL
+//     light tiles, each on a 64-thread group with K = 4 (fewest instructions); groups synchronise on their own
+//     named barrier.  Measured on B200: a uniform K = 4 leaves the SMs idle > 50 % of the kernel waiting for a few
+//     deep tiles, a uniform K = 1 is issue-bound (profiles/r01).
 //   * splat records (48 B, three 16-B quads) are GATHERED straight into shared memory with cp.async (LDGSTS),
 //     double buffered one chunk ahead, ids one further chunk ahead: no register staging, no exposed L2 latency.
+//   * forward records, per sorted instance, which 16x2 pixel strips of its tile it contributed to (one byte);
+//     backward skips every (splat, warp) pair whose strips are all clear before doing any arithmetic.
 //   * backward: per-lane partial sums over the K pixels collapse to three moments (S0,S1,S2) because dx is
 //     shared; nine per-splat gradient components are then reduced across the warp with a 14-shuffle
 //     multi-value butterfly (instead of 45 shuffles or 9*32 atomics) and leave the SM as ONE 9-lane RED.ADD.F32
-//     per (warp, splat); warps whose pixels all rejected the splat skip the reduction entirely (vote).
+//     per (warp, splat).
 // Tensor cores are not used: there is no dense contraction on this path (north_star).
 #include <cstdlib>
 
@@ -22,6 +29,10 @@ namespace gab {
 
 #define LOG2E 1.4426950408889634f
 #define ALPHA_MIN (1.0f / 255.0f)
+#define FULLMASK 0xffffffffu
+// SplatRec stores the conic pre-scaled for the exponent in log2 units: (A',B',C') = (-A/2, -B, -C/2) * log2(e)
+#define CONIC_UNSCALE_AC (-2.0f / LOG2E)
+#define CONIC_UNSCALE_B (-1.0f / LOG2E)
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -48,28 +59,46 @@ __device__ __forceinline__ void gather_rec(SplatRec* dst, const SplatRec* src) {
   cp_async16(&dst->q2, &src->q2);
 }
 
+// Barrier of one thread group (NT threads, hardware barrier `id`); id 0 with NT = blockDim is __syncthreads().
+template <int NT>
+struct GroupBarrier {
+  int id;
+  __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NT) : "memory"); }
+  __device__ __forceinline__ bool sync_and(bool pred) const {
+    unsigned r;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %1, 0;\n\tbar.red.and.pred p, %2, %3, q;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(r)
+        : "r"((unsigned)pred), "r"(id), "n"(NT)
+        : "memory");
+    return r != 0;
+  }
+};
+
 // =====================================================================================================
-// Forward
+// Forward: one tile on a group of NT = 256/K threads (tl = thread index inside the group)
 // =====================================================================================================
 template <int K>
-__global__ void __launch_bounds__(256 / K) blend_forward_kernel(int W, int H, int gx, const uint2* __restrict__ ranges,
-                                                                const uint32_t* __restrict__ point_list,
-                                                                const SplatRec* __restrict__ rec,
-                                                                const float* __restrict__ bg,
-                                                                float* __restrict__ out_color,
-                                                                float* __restrict__ final_T,
-                                                                uint32_t* __restrict__ n_contrib) {
+__device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
+                                             SplatRec* buf1, uint32_t* smask, int W, int H, int gx,
+                                             const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                             const SplatRec* __restrict__ rec, const float* __restrict__ bg,
+                                             float* __restrict__ out_color, float* __restrict__ final_T,
+                                             uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ strip_mask) {
   constexpr int NT = 256 / K;
-  __shared__ SplatRec buf[2][NT];
-  const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
-  const int t = threadIdx.x;
-  const int pixx = tx * GAB_TILE + (t & 15);
-  const int pixy0 = ty * GAB_TILE + (t >> 4) * K;
-  const float fx = (float)pixx, fy0 = (float)pixy0;
+  const int lane = tl & 31;
+  const int pixx = tx * GAB_TILE + (tl & 15);
+  const int pixy0 = ty * GAB_TILE + (tl >> 4) * K;
+  const float fx = (float)pixx;
+  float fy[K];  // pixel rows as floats: dy = py - fy[i] is then independent of K (same bits on every tile schedule)
+#pragma unroll
+  for (int i = 0; i < K; i++) fy[i] = (float)(pixy0 + i);
   const uint2 range = ranges[tile];
   const int n = (int)(range.y - range.x);
   const uint32_t* ids = point_list + range.x;
+  const bool want_mask = strip_mask != nullptr;
+  smask[tl] = 0;
 
   float T[K], Cr[K], Cg[K], Cb[K];
   uint32_t last[K];
@@ -83,37 +112,44 @@ __global__ void __launch_bounds__(256 / K) blend_forward_kernel(int W, int H, in
 
   const int nchunks = (n + NT - 1) / NT;
   // prologue: ids of chunk 0 -> gather chunk 0; ids of chunk 1 in flight
-  uint32_t id_next = (t < n) ? ids[t] : 0xffffffffu;
-  if (id_next != 0xffffffffu) gather_rec(&buf[0][t], rec + id_next);
+  uint32_t id_next = (tl < n) ? ids[tl] : 0xffffffffu;
+  if (id_next != 0xffffffffu) gather_rec(&buf0[tl], rec + id_next);
   cp_async_commit();
-  id_next = (NT + t < n) ? ids[NT + t] : 0xffffffffu;
+  id_next = (NT + tl < n) ? ids[NT + tl] : 0xffffffffu;
 
   for (int c = 0; c < nchunks; c++) {
-    if (c + 1 < nchunks && id_next != 0xffffffffu) gather_rec(&buf[(c + 1) & 1][t], rec + id_next);
+    SplatRec* nxt = ((c + 1) & 1) ? buf1 : buf0;
+    if (c + 1 < nchunks && id_next != 0xffffffffu) gather_rec(&nxt[tl], rec + id_next);
     cp_async_commit();
     {
-      const int p = (c + 2) * NT + t;
+      const int p = (c + 2) * NT + tl;
       id_next = (p < n) ? ids[p] : 0xffffffffu;
     }
     cp_async_wait<1>();
-    if (__syncthreads_and(done == ALL)) break;  // also publishes chunk c to the CTA
-    const SplatRec* cur = buf[c & 1];
+    if (bar.sync_and(done == ALL)) break;  // also publishes chunk c to the group
+    const SplatRec* cur = (c & 1) ? buf1 : buf0;
     const int cnt = min(NT, n - c * NT);
     const uint32_t pos0 = (uint32_t)(c * NT);
-    for (int j = 0; j < cnt; j++) {
-      if (done == ALL) break;
+    // Strip bookkeeping for the backward pass, ~2 instructions per splat: every lane records, one bit per splat of
+    // the current 32-splat group, whether its pixels of strip s contributed; at the end of the group one REDUX.OR
+    // per strip turns the lanes' words into "strip s was touched by splat gbase+L" and lane L publishes splat L.
+    constexpr int S = (K + 1) / 2;  // strips a lane's pixels belong to
+    uint32_t lb[S];
+#pragma unroll
+    for (int s_ = 0; s_ < S; s_++) lb[s_] = 0;
+    int gbase = 0;
+    bool stop = false;
+    for (int j = 0; j < cnt && !stop; j++) {
+      gbase = j & ~31;
       const float4 q0 = cur[j].q0;
       const float4 q1 = cur[j].q1;
-      const float cb = cur[j].q2.x;
-      const float dx = q0.x - fx, dy0 = q0.y - fy0;
-      const float p0 = (-0.5f * LOG2E) * q0.z * dx * dx;
-      const float qq = (-LOG2E) * q0.w * dx;
-      const float hh = (-0.5f * LOG2E) * q1.x;
+      const float dx = q0.x - fx;
+      const float tA = q0.z * dx;            // conic pre-scaled by preprocess: pw = A' dx^2 + B' dx dy + C' dy^2 (log2 units)
       const float op = q1.y;
 #pragma unroll
       for (int i = 0; i < K; i++) {
-        const float dy = dy0 - (float)i;
-        const float pw = fmaf(dy, fmaf(hh, dy, qq), p0);
+        const float dy = q0.y - fy[i];
+        const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
         const float alpha = fminf(0.99f, op * ex2_approx(pw));
         if (!((done >> i) & 1u) && pw <= 0.f && alpha >= ALPHA_MIN) {
           const float test_T = T[i] * (1.f - alpha);
@@ -123,14 +159,40 @@ __global__ void __launch_bounds__(256 / K) blend_forward_kernel(int W, int H, in
             const float w = alpha * T[i];
             Cr[i] = fmaf(q1.z, w, Cr[i]);
             Cg[i] = fmaf(q1.w, w, Cg[i]);
-            Cb[i] = fmaf(cb, w, Cb[i]);
+            Cb[i] = fmaf(cur[j].q2.x, w, Cb[i]);
             T[i] = test_T;
             last[i] = pos0 + (uint32_t)j + 1u;
+            lb[i >> 1] |= 1u << (j & 31);
           }
         }
       }
+      if ((j & 31) == 31 || j == cnt - 1) {  // warp-uniform
+        if (want_mask) {
+          uint32_t wh = 0;
+          const int w_ = tl >> 5;
+#pragma unroll
+          for (int s_ = 0; s_ < S; s_++) {
+            if (K == 1) {
+              const uint32_t r = __reduce_or_sync(FULLMASK, lb[0]);
+              wh |= ((r >> lane) & 1u) << w_;
+            } else {
+              const uint32_t rlo = __reduce_or_sync(FULLMASK, lane < 16 ? lb[s_] : 0u);
+              const uint32_t rhi = __reduce_or_sync(FULLMASK, lane < 16 ? 0u : lb[s_]);
+              wh |= ((rlo >> lane) & 1u) << (w_ * K + s_);
+              wh |= ((rhi >> lane) & 1u) << (w_ * K + K / 2 + s_);
+            }
+            lb[s_] = 0;
+          }
+          if (wh) atomicOr(&smask[gbase + lane], wh);
+        }
+        stop = __all_sync(FULLMASK, done == ALL);  // this warp's pixels are all saturated
+      }
     }
-    __syncthreads();  // everyone is done with buf[c&1] before chunk c+2 is gathered into it
+    bar.sync();  // everyone is done with this buffer before chunk c+2 is gathered into it; masks complete
+    if (want_mask && tl < cnt) {
+      strip_mask[range.x + (uint32_t)(c * NT + tl)] = (uint8_t)smask[tl];
+      smask[tl] = 0;
+    }
   }
   cp_async_wait<0>();
 
@@ -152,24 +214,60 @@ __global__ void __launch_bounds__(256 / K) blend_forward_kernel(int W, int H, in
   }
 }
 
+// CTA = 256 threads.  The first CTAs take KH heavy tiles each on 256/KH threads (KH = 1: all eight warps on one
+// tile); the following CTAs take four light tiles each, one per 64-thread group, K = 4.
+template <int KH>
+__global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx, int tiles,
+                                                            const uint2* __restrict__ ranges,
+                                                            const uint32_t* __restrict__ order,
+                                                            const uint32_t* __restrict__ order_info,
+                                                            const uint32_t* __restrict__ point_list,
+                                                            const SplatRec* __restrict__ rec,
+                                                            const float* __restrict__ bg, float* __restrict__ out_color,
+                                                            float* __restrict__ final_T,
+                                                            uint32_t* __restrict__ n_contrib,
+                                                            uint8_t* __restrict__ strip_mask) {
+  __shared__ SplatRec buf[2][256];
+  __shared__ uint32_t smask[256];
+  constexpr int GH = KH;  // heavy tiles per CTA (256/KH threads each)
+  constexpr int NTH = 256 / KH;
+  const int nh = (int)order_info[0];
+  const int heavy_ctas = (nh + GH - 1) / GH;
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (b < heavy_ctas) {
+    const int g = t / NTH, slot = b * GH + g;
+    if (slot >= nh) return;
+    forward_tile<KH>((int)order[slot], t - g * NTH, GroupBarrier<NTH>{GH == 1 ? 0 : 1 + g}, buf[0] + g * NTH,
+                     buf[1] + g * NTH, smask + g * NTH, W, H, gx, ranges, point_list, rec, bg, out_color, final_T,
+                     n_contrib, strip_mask);
+  } else {
+    const int g = t >> 6, slot = nh + 4 * (b - heavy_ctas) + g;
+    if (slot >= tiles) return;
+    forward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
+                    smask + g * 64, W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib, strip_mask);
+  }
+}
+
 static int env_int(const char* name, int dflt) {
   const char* s = getenv(name);
   return s ? atoi(s) : dflt;
 }
 
-void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
-                          const float* bg, float* out_color, float* final_T, uint32_t* n_contrib,
-                          cudaStream_t stream) {
+void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
+                          const uint32_t* point_list, const SplatRec* rec, const float* bg, float* out_color,
+                          float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, cudaStream_t stream) {
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
-  static const int K = env_int("GAB200_FWD_K", 4);
-  switch (K) {
-    case 1: blend_forward_kernel<1><<<tiles, 256, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib); break;
-    case 2: blend_forward_kernel<2><<<tiles, 128, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib); break;
-    case 8: blend_forward_kernel<8><<<tiles, 32, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib); break;
-    default: blend_forward_kernel<4><<<tiles, 64, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib); break;
-  }
+  static const int KH = env_int("GAB200_FWD_KH", 1);
+  // upper bound on CTAs: every tile heavy; surplus CTAs exit at once
+  const int grid = tiles;
+  if (KH == 2)
+    blend_forward_kernel<2><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
+                                                      out_color, final_T, n_contrib, strip_mask);
+  else
+    blend_forward_kernel<1><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
+                                                      out_color, final_T, n_contrib, strip_mask);
   count_launch();
 }
 
@@ -179,56 +277,58 @@ void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* poi
 // Multi-value butterfly: reduces v[0..7] across the 32 lanes with 4+2+1+1+1 = 9 shuffles.  On return every lane
 // holds the warp total of component (lane >> 2).
 __device__ __forceinline__ float warp_reduce8(const float v[8], int lane) {
-  constexpr unsigned FULL = 0xffffffffu;
   float w[4], u[2];
   const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     const float send = h16 ? v[i] : v[i + 4];
     const float keep = h16 ? v[i + 4] : v[i];
-    w[i] = keep + __shfl_xor_sync(FULL, send, 16);
+    w[i] = keep + __shfl_xor_sync(FULLMASK, send, 16);
   }
 #pragma unroll
   for (int i = 0; i < 2; i++) {
     const float send = h8 ? w[i] : w[i + 2];
     const float keep = h8 ? w[i + 2] : w[i];
-    u[i] = keep + __shfl_xor_sync(FULL, send, 8);
+    u[i] = keep + __shfl_xor_sync(FULLMASK, send, 8);
   }
   const float send = h4 ? u[0] : u[1];
   const float keep = h4 ? u[1] : u[0];
-  float r = keep + __shfl_xor_sync(FULL, send, 4);
-  r += __shfl_xor_sync(FULL, r, 2);
-  r += __shfl_xor_sync(FULL, r, 1);
+  float r = keep + __shfl_xor_sync(FULLMASK, send, 4);
+  r += __shfl_xor_sync(FULLMASK, r, 2);
+  r += __shfl_xor_sync(FULLMASK, r, 1);
   return r;
 }
 __device__ __forceinline__ float warp_reduce1(float v) {
-  constexpr unsigned FULL = 0xffffffffu;
 #pragma unroll
-  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULL, v, m);
+  for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULLMASK, v, m);
   return v;
 }
 
 template <int K>
-__global__ void __launch_bounds__(256 / K) blend_backward_kernel(int W, int H, int gx, const uint2* __restrict__ ranges,
-                                                                 const uint32_t* __restrict__ point_list,
-                                                                 const SplatRec* __restrict__ rec,
-                                                                 const float* __restrict__ bg,
-                                                                 const float* __restrict__ final_T,
-                                                                 const uint32_t* __restrict__ n_contrib,
-                                                                 const float* __restrict__ dL_dpix,
-                                                                 float* __restrict__ g2d) {
+__device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
+                                              SplatRec* buf1, uint32_t* bid0, uint32_t* bid1, uint32_t* bm0,
+                                              uint32_t* bm1, int* s_max, int W, int H, int gx,
+                                              const uint2* __restrict__ ranges,
+                                              const uint32_t* __restrict__ point_list,
+                                              const SplatRec* __restrict__ rec, const float* __restrict__ bg,
+                                              const float* __restrict__ final_T,
+                                              const uint32_t* __restrict__ n_contrib,
+                                              const float* __restrict__ dL_dpix,
+                                              const uint8_t* __restrict__ strip_mask, float* __restrict__ g2d) {
   constexpr int NT = 256 / K;
-  __shared__ SplatRec buf[2][NT];
-  __shared__ uint32_t buf_id[2][NT];
-  __shared__ int s_max;
-  const int tile = blockIdx.x;
   const int tx = tile % gx, ty = tile / gx;
-  const int t = threadIdx.x, lane = t & 31;
-  const int pixx = tx * GAB_TILE + (t & 15);
-  const int pixy0 = ty * GAB_TILE + (t >> 4) * K;
-  const float fx = (float)pixx, fy0 = (float)pixy0;
+  const int lane = tl & 31;
+  const int pixx = tx * GAB_TILE + (tl & 15);
+  const int pixy0 = ty * GAB_TILE + (tl >> 4) * K;
+  const float fx = (float)pixx;
+  float fy[K];
+#pragma unroll
+  for (int i = 0; i < K; i++) fy[i] = (float)(pixy0 + i);
   const uint2 range = ranges[tile];
   const uint32_t* ids = point_list + range.x;
+  const uint8_t* masks = strip_mask + range.x;
+  // strips (rows 2s, 2s+1 of the tile) owned by this warp: 2K rows = K strips starting at warp*K
+  const uint32_t my_strips = ((1u << K) - 1u) << ((tl >> 5) * K);
   const size_t HW = (size_t)H * W;
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
 
@@ -253,54 +353,62 @@ __global__ void __launch_bounds__(256 / K) blend_backward_kernel(int W, int H, i
     my_max = max(my_max, nc[i]);
   }
   // the tile only needs instances [0, max n_contrib): nothing behind the last contributor of any pixel matters
-  if (t == 0) s_max = 0;
-  __syncthreads();
-  my_max = __reduce_max_sync(0xffffffffu, my_max);
-  if (lane == 0 && my_max > 0) atomicMax(&s_max, my_max);
-  __syncthreads();
-  const int n = s_max;
+  if (tl == 0) *s_max = 0;
+  bar.sync();
+  my_max = __reduce_max_sync(FULLMASK, my_max);
+  if (lane == 0 && my_max > 0) atomicMax(s_max, my_max);
+  bar.sync();
+  const int n = *s_max;
   if (n == 0) return;
   const int nchunks = (n + NT - 1) / NT;
   const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;
 
   // reverse walk: chunk c covers positions n-1-c*NT-j (j = 0..NT-1)
-  uint32_t id_next = (t < n) ? ids[n - 1 - t] : 0xffffffffu;
-  if (id_next != 0xffffffffu) gather_rec(&buf[0][t], rec + id_next);
-  buf_id[0][t] = id_next;
+  uint32_t id_next = (tl < n) ? ids[n - 1 - tl] : 0xffffffffu;
+  uint32_t mask_next = (tl < n) ? masks[n - 1 - tl] : 0u;
+  if (id_next != 0xffffffffu && mask_next != 0) gather_rec(&buf0[tl], rec + id_next);
+  bid0[tl] = id_next;
+  bm0[tl] = mask_next;
   cp_async_commit();
-  id_next = (NT + t < n) ? ids[n - 1 - NT - t] : 0xffffffffu;
+  id_next = (NT + tl < n) ? ids[n - 1 - NT - tl] : 0xffffffffu;
+  mask_next = (NT + tl < n) ? masks[n - 1 - NT - tl] : 0u;
 
   for (int c = 0; c < nchunks; c++) {
+    const bool odd = (c & 1) != 0;
     if (c + 1 < nchunks) {
-      if (id_next != 0xffffffffu) gather_rec(&buf[(c + 1) & 1][t], rec + id_next);
-      buf_id[(c + 1) & 1][t] = id_next;
+      SplatRec* nb = odd ? buf0 : buf1;
+      if (id_next != 0xffffffffu && mask_next != 0) gather_rec(&nb[tl], rec + id_next);
+      (odd ? bid0 : bid1)[tl] = id_next;
+      (odd ? bm0 : bm1)[tl] = mask_next;
     }
     cp_async_commit();
     {
-      const int p = (c + 2) * NT + t;
+      const int p = (c + 2) * NT + tl;
       id_next = (p < n) ? ids[n - 1 - p] : 0xffffffffu;
+      mask_next = (p < n) ? masks[n - 1 - p] : 0u;
     }
     cp_async_wait<1>();
-    __syncthreads();
-    const SplatRec* cur = buf[c & 1];
-    const uint32_t* cur_id = buf_id[c & 1];
+    bar.sync();
+    const SplatRec* cur = odd ? buf1 : buf0;
+    const uint32_t* cur_id = odd ? bid1 : bid0;
+    const uint32_t* cur_mask = odd ? bm1 : bm0;
     const int cnt = min(NT, n - c * NT);
     for (int j = 0; j < cnt; j++) {
+      // the forward recorded which pixel strips this splat contributed to: no strip of this warp -> nothing to do
+      if ((cur_mask[j] & my_strips) == 0) continue;
       const int pos = n - 1 - c * NT - j;  // 0-based position in the tile's list; contributes to pixel iff pos < nc
       const float4 q0 = cur[j].q0;
       const float4 q1 = cur[j].q1;
       const float cbl = cur[j].q2.x;
-      const float dx = q0.x - fx, dy0 = q0.y - fy0;
-      const float A = q0.z, B = q0.w, C = q1.x, op = q1.y;
-      const float p0 = (-0.5f * LOG2E) * A * dx * dx;
-      const float qq = (-LOG2E) * B * dx;
-      const float hh = (-0.5f * LOG2E) * C;
+      const float dx = q0.x - fx;
+      const float tA = q0.z * dx;  // conic is stored pre-scaled: (A',B',C') = (-A/2, -B, -C/2) * log2(e)
+      const float A = q0.z * CONIC_UNSCALE_AC, B = q0.w * CONIC_UNSCALE_B, C = q1.x * CONIC_UNSCALE_AC, op = q1.y;
       float S0 = 0.f, S1 = 0.f, S2 = 0.f, go = 0.f, gr = 0.f, gg = 0.f, gb = 0.f;
       bool any = false;
 #pragma unroll
       for (int i = 0; i < K; i++) {
-        const float dy = dy0 - (float)i;
-        const float pw = fmaf(dy, fmaf(hh, dy, qq), p0);
+        const float dy = q0.y - fy[i];
+        const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
         const float G = ex2_approx(pw);
         const float alpha = fminf(0.99f, op * G);
         if (pos < nc[i] && pw <= 0.f && alpha >= ALPHA_MIN) {
@@ -321,14 +429,14 @@ __global__ void __launch_bounds__(256 / K) blend_backward_kernel(int W, int H, i
           ag[i] = fmaf(alpha, q1.w - ag[i], ag[i]);
           ab[i] = fmaf(alpha, cbl - ab[i], ab[i]);
           go = fmaf(G, dLda, go);
-          const float s = G * op * dLda;  // G * dL/dG
-          const float sd = s * dy;
-          S0 += s;
+          const float s_ = G * op * dLda;  // G * dL/dG
+          const float sd = s_ * dy;
+          S0 += s_;
           S1 += sd;
           S2 = fmaf(sd, dy, S2);
         }
       }
-      if (!__any_sync(0xffffffffu, any)) continue;
+      if (!__any_sync(FULLMASK, any)) continue;
       float v[8];
       v[0] = (-A * dx * S0 - B * S1) * half_W;  // dL/dmean2D.x (NDC units)
       v[1] = (-C * S1 - B * dx * S0) * half_H;  // dL/dmean2D.y
@@ -346,24 +454,52 @@ __global__ void __launch_bounds__(256 / K) blend_backward_kernel(int W, int H, i
       else if (lane == 1)
         atomicAdd(g2d + (size_t)id * GAB_G2D_STRIDE + 8, r1);
     }
-    __syncthreads();
+    bar.sync();
   }
   cp_async_wait<0>();
 }
 
-void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
-                           const float* bg, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
-                           float* g2d, cudaStream_t stream) {
+// CTA = 128 threads: CTAs [0, n_heavy) take one heavy tile with K = 2 (four warps); the rest take two light tiles
+// each, one per 64-thread group with K = 4.
+__global__ void __launch_bounds__(128) blend_backward_kernel(int W, int H, int gx, int tiles,
+                                                             const uint2* __restrict__ ranges,
+                                                             const uint32_t* __restrict__ order,
+                                                             const uint32_t* __restrict__ order_info,
+                                                             const uint32_t* __restrict__ point_list,
+                                                             const SplatRec* __restrict__ rec,
+                                                             const float* __restrict__ bg,
+                                                             const float* __restrict__ final_T,
+                                                             const uint32_t* __restrict__ n_contrib,
+                                                             const float* __restrict__ dL_dpix,
+                                                             const uint8_t* __restrict__ strip_mask,
+                                                             float* __restrict__ g2d) {
+  __shared__ SplatRec buf[2][128];
+  __shared__ uint32_t bid[2][128];
+  __shared__ uint32_t bm[2][128];
+  __shared__ int s_max[2];
+  const int nh = (int)order_info[1];
+  const int b = blockIdx.x, t = threadIdx.x;
+  if (b < nh) {
+    backward_tile<2>((int)order[b], t, GroupBarrier<128>{0}, buf[0], buf[1], bid[0], bid[1], bm[0], bm[1], &s_max[0], W,
+                     H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+  } else {
+    const int g = t >> 6, slot = nh + 2 * (b - nh) + g;
+    if (slot >= tiles) return;
+    backward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
+                     bid[0] + g * 64, bid[1] + g * 64, bm[0] + g * 64, bm[1] + g * 64, &s_max[g], W, H, gx, ranges,
+                     point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+  }
+}
+
+void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
+                           const uint32_t* point_list, const SplatRec* rec, const float* bg, const float* final_T,
+                           const uint32_t* n_contrib, const float* dL_dpix, const uint8_t* strip_mask, float* g2d,
+                           cudaStream_t stream) {
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
-  static const int K = env_int("GAB200_BWD_K", 4);
-  switch (K) {
-    case 1: blend_backward_kernel<1><<<tiles, 256, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, g2d); break;
-    case 2: blend_backward_kernel<2><<<tiles, 128, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, g2d); break;
-    case 8: blend_backward_kernel<8><<<tiles, 32, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, g2d); break;
-    default: blend_backward_kernel<4><<<tiles, 64, 0, stream>>>(W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, g2d); break;
-  }
+  blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
+                                                   final_T, n_contrib, dL_dpix, strip_mask, g2d);
   count_launch();
 }
 

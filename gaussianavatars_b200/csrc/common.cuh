@@ -12,11 +12,22 @@ namespace gab {
 
 // Per-splat screen-space record written by preprocess and gathered by both blend kernels.
 // 48 B = three 16-B quads so that one splat is three LDG.128 / cp.async.16:
-//   q0 = (px, py, conic.xx, conic.xy)   q1 = (conic.yy, opacity, r, g)   q2 = (b, depth, radius bits, tiles bits)
+//   q0 = (px, py, A', B')   q1 = (C', opacity, r, g)   q2 = (b, rx, ry, 0)
+// with the conic pre-scaled for the blend exponent in log2 units: (A',B',C') = (-conic.xx/2, -conic.xy, -conic.yy/2)*log2 e
+// (rx, ry) = half extents of the axis-aligned box around the region where the splat can reach alpha >= 1/255
+// (negative: nowhere) -- the blend-forward warps use it to skip splats that cannot touch their pixel strip.
 struct __align__(16) SplatRec {
   float4 q0, q1, q2;
 };
 static_assert(sizeof(SplatRec) == 48, "SplatRec must be 48 bytes");
+
+// Per-splat binning data (read by key emission and by preprocess-backward only): depth, 3-sigma radius, tile count.
+struct __align__(16) SplatAux {
+  float depth;
+  int radius;
+  uint32_t tiles;
+  uint32_t pad;
+};
 
 // Per-splat 2-D gradient record accumulated by blend-backward (RED.ADD) and consumed by preprocess-backward:
 //   (dL/dndc.x, dL/dndc.y, dL/dconic.xx, dL/dconic.xy, dL/dconic.yy, dL/dopacity, dL/dr, dL/dg, dL/db, pad*3)

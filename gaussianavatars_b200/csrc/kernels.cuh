@@ -69,14 +69,15 @@ struct TileSpan {
 };
 
 // ---- launchers (each counts its launches) ----
-void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, uint32_t* tiles_touched, uint8_t* clamped,
-                       cudaStream_t stream);
+void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
+                       uint8_t* clamped, cudaStream_t stream);
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
-void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, int exact_binning, cudaStream_t stream);
+void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
+                      uint64_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
 void launch_tile_ranges(int64_t N, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream);
 
 // binning.cu (cub)
 size_t scan_temp_bytes(int P);
@@ -86,14 +87,23 @@ cudaError_t run_sort(void* temp, size_t temp_bytes, uint64_t* keys_a, uint64_t* 
                      uint32_t* vals_b, int64_t N, int end_bit, int* selector_out, cudaStream_t stream);
 
 // blend.cu
-void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
-                          const float* bg, float* out_color, float* final_T, uint32_t* n_contrib, cudaStream_t stream);
-void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* point_list, const SplatRec* rec,
+void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
+                          const uint32_t* point_list, const SplatRec* rec,
+                          const float* bg, float* out_color, float* final_T, uint32_t* n_contrib, uint8_t* strip_mask,
+                          cudaStream_t stream);
+void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
+                           const uint32_t* point_list, const SplatRec* rec,
                            const float* bg, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,
-                           float* g2d, cudaStream_t stream);
+                           const uint8_t* strip_mask, float* g2d, cudaStream_t stream);
 
 // preprocess_bwd.cu
-void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const uint8_t* clamped,
-                                const float* g2d, cudaStream_t stream);
+void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const SplatAux* aux,
+                                const uint8_t* clamped, const float* g2d, cudaStream_t stream);
+
+// face_frame.cu
+void launch_face_frame_forward(int F, const float* verts, const int32_t* faces, float* fc, float* fR, float* fs,
+                               cudaStream_t stream);
+void launch_face_frame_backward(int F, const float* verts, const int32_t* faces, const float* g_fc, const float* g_fR,
+                                const float* g_fs, float* g_verts, cudaStream_t stream);
 
 }  // namespace gab

@@ -7,11 +7,16 @@
 // Replaces, in ONE kernel (SURVEY.md 2.4 K1 + the eager getters of 2.4(b)):
 //   scene/gaussian_model.py:113-160   get_xyz / get_rotation / get_scaling / get_opacity / get_features
 //   diff_gaussian_rasterization preprocessCUDA (absent submodule; behaviour: SURVEY.md Appendix B.1)
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "splat_math.cuh"
 
 namespace gab {
+
+#define REC_SCALE_AC (-0.5f * 1.4426950408889634f)
+#define REC_SCALE_B (-1.4426950408889634f)
 
 __device__ __forceinline__ void stage_camera(const gab200_forward_args& a, Camera& cam) {
   int t = threadIdx.x;
@@ -25,13 +30,26 @@ __device__ __forceinline__ void stage_camera(const gab200_forward_args& a, Camer
 // K1: fused bind + activate + project + EWA + SH->RGB.  One thread per splat.
 // =====================================================================================================
 template <bool BOUND>
-__global__ void __launch_bounds__(256) preprocess_kernel(gab200_forward_args a, SplatRec* __restrict__ rec,
-                                                         uint32_t* __restrict__ tiles_touched,
-                                                         uint8_t* __restrict__ clamped, int exact_binning) {
+__global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args a, SplatRec* __restrict__ rec,
+                                                            SplatAux* __restrict__ aux,
+                                                            uint32_t* __restrict__ tiles_touched,
+                                                            uint8_t* __restrict__ clamped, int exact_binning) {
   __shared__ Camera cam;
+  __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   stage_camera(a, cam);
+  // SH coefficients of the block's splats: coalesced 128-bit loads -> shared memory (row stride odd: conflict-free)
+  const int sh_width = BOUND ? 3 * (a.sh_coeffs - 1) : 3 * a.sh_coeffs;
+  const int sh_stride = sh_width | 1;
+  const float* sh_src = BOUND ? a.sh_rest : a.shs;
+  const bool use_sh = a.colors_precomp == nullptr && sh_src != nullptr && sh_width > 0;
+  if (use_sh) {
+    const int row0 = blockIdx.x * PRE_NT;
+    stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, min(PRE_NT, a.P - row0), sh_width, sh_stride);
+    __syncthreads();
+  }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.P) return;
+  const float* my_sh = sh_s + threadIdx.x * sh_stride;
   const int W = a.image_width, H = a.image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
 
@@ -40,6 +58,7 @@ __global__ void __launch_bounds__(256) preprocess_kernel(gab200_forward_args a, 
   out.q1 = make_float4(0.f, 0.f, 0.f, 0.f);
   out.q2 = make_float4(0.f, 0.f, 0.f, 0.f);
   int radius_out = 0;
+  float depth_out = 0.f;
   uint32_t tiles_out = 0;
   uint8_t clamp_bits = 0;
 
@@ -136,14 +155,14 @@ __global__ void __launch_bounds__(256) preprocess_kernel(gab200_forward_args a, 
             acc[0] = acc[0] + B[0] * dc[0];
             acc[1] = acc[1] + B[0] * dc[1];
             acc[2] = acc[2] + B[0] * dc[2];
-            const float* rest = a.sh_rest + (size_t)i * (a.sh_coeffs - 1) * 3;
+            const float* rest = my_sh;
             for (int k = 1; k < nb; k++) {
               acc[0] = acc[0] + B[k] * rest[3 * (k - 1) + 0];
               acc[1] = acc[1] + B[k] * rest[3 * (k - 1) + 1];
               acc[2] = acc[2] + B[k] * rest[3 * (k - 1) + 2];
             }
           } else {
-            const float* sh = a.shs + (size_t)i * a.sh_coeffs * 3;
+            const float* sh = my_sh;
             for (int k = 0; k < nb; k++) {
               acc[0] = acc[0] + B[k] * sh[3 * k + 0];
               acc[1] = acc[1] + B[k] * sh[3 * k + 1];
@@ -158,12 +177,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(gab200_forward_args a, 
           }
         }
         radius_out = (int)my_radius;
-        out.q0 = make_float4(px, py, conic_x, conic_y);
-        out.q1 = make_float4(conic_z, opacity, rgb[0], rgb[1]);
+        // conic pre-scaled for the blend kernels' exponent in log2 units: pw = A' dx^2 + B' dx dy + C' dy^2
+        out.q0 = make_float4(px, py, conic_x * REC_SCALE_AC, conic_y * REC_SCALE_B);
+        out.q1 = make_float4(conic_z * REC_SCALE_AC, opacity, rgb[0], rgb[1]);
+        // the span test must see exactly the values key emission will read back from the record
+        TileSpan span(px, py, (conic_x * REC_SCALE_AC) / REC_SCALE_AC, (conic_y * REC_SCALE_B) / REC_SCALE_B,
+                      (conic_z * REC_SCALE_AC) / REC_SCALE_AC, opacity, x0, x1);
+        const float ext_x = !span.any ? -1.f : (span.full ? 1.0e30f : span.dxmax + 0.02f);
+        const float ext_y = !span.any ? -1.f : (span.full ? 1.0e30f : span.ymax + 0.02f);
         if (exact_binning) {
           tiles_out = (uint32_t)((y1 - y0) * (x1 - x0));
         } else {
-          TileSpan span(px, py, conic_x, conic_y, conic_z, opacity, x0, x1);
           uint32_t cnt = 0;
           if (span.any)
             for (int ty = y0; ty < y1; ty++) {
@@ -173,24 +197,28 @@ __global__ void __launch_bounds__(256) preprocess_kernel(gab200_forward_args a, 
             }
           tiles_out = cnt;
         }
-        out.q2 = make_float4(rgb[2], t.z, __int_as_float(radius_out), __int_as_float((int)tiles_out));
+        out.q2 = make_float4(rgb[2], ext_x, ext_y, 0.f);
+        depth_out = t.z;
       }
     }
   }
   rec[i] = out;
+  SplatAux ax;
+  ax.depth = depth_out; ax.radius = radius_out; ax.tiles = tiles_out; ax.pad = 0;
+  aux[i] = ax;
   a.radii[i] = radius_out;
   tiles_touched[i] = tiles_out;
   if (clamped != nullptr) clamped[i] = clamp_bits;
 }
 
-void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, uint32_t* tiles_touched, uint8_t* clamped,
-                       cudaStream_t stream) {
-  const int threads = 256, blocks = (a.P + threads - 1) / threads;
+void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
+                       uint8_t* clamped, cudaStream_t stream) {
+  const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, tiles_touched, clamped, a.exact_binning);
+    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, a.exact_binning);
   else
-    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, tiles_touched, clamped, a.exact_binning);
+    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, a.exact_binning);
   count_launch();
 }
 
@@ -248,14 +276,21 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
 }
 
 // =====================================================================================================
-// K3: tile|depth key emission.  One WARP per 32 splats; the lanes cooperate on each splat's tile list so that
-// stores are coalesced and a 256-tile splat does not serialise one thread.  Emission order inside a splat is
-// row-major (y, then x) from offsets[i-1] -- identical to the reference, so the stable sort's tie order is too.
+// K3: tile|depth key emission.  Emission order inside a splat is row-major (y, then x) from offsets[i-1] --
+// identical to the reference, so the stable sort's tie order is too.
+//   exact list  : one WARP per 32 splats, lanes cooperate on each splat's rectangle (a 1000-tile splat does not
+//                 serialise one thread; stores coalesce).
+//   culled list : one THREAD per splat walks its rows (a few sqrt per row, ~4 rows on average); splats with many
+//                 rows are handed to the whole warp afterwards, one row per lane.
 // =====================================================================================================
+#define EMIT_HEAVY_ROWS 12
+
 __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, const SplatRec* __restrict__ rec,
+                                                        const SplatAux* __restrict__ aux,
                                                         const uint32_t* __restrict__ offsets,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                         int exact_binning) {
+  constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int i = warp_global * 32 + lane;
@@ -263,61 +298,97 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   int radius = 0;
   uint32_t ntiles = 0, off = 0;
   if (i < P) {
-    const float4 q2 = rec[i].q2;
-    ntiles = (uint32_t)__float_as_int(q2.w);
+    const SplatAux ax = aux[i];
+    ntiles = ax.tiles;
     if (ntiles) {
       const float4 q0 = rec[i].q0;
       const float4 q1 = rec[i].q1;
-      px = q0.x; py = q0.y; cA = q0.z; cB = q0.w; cC = q1.x; op = q1.y;
-      depth = q2.y;
-      radius = __float_as_int(q2.z);
+      px = q0.x; py = q0.y; op = q1.y;
+      cA = q0.z / REC_SCALE_AC; cB = q0.w / REC_SCALE_B; cC = q1.x / REC_SCALE_AC;  // undo the blend pre-scale
+      depth = ax.depth;
+      radius = ax.radius;
       off = (i == 0) ? 0u : offsets[i - 1];
     }
   }
-  uint32_t todo = __ballot_sync(0xffffffffu, ntiles != 0);
-  while (todo) {
-    const int src = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
-    const int srad = __shfl_sync(0xffffffffu, radius, src);
-    const uint32_t soff = __shfl_sync(0xffffffffu, off, src);
-    const uint32_t sdepth = __float_as_uint(__shfl_sync(0xffffffffu, depth, src));
-    const uint32_t sid = (uint32_t)(warp_global * 32 + src);
-    int x0, y0, x1, y1;
-    tile_rect(spx, spy, srad, gx, gy, x0, y0, x1, y1);
-    if (exact_binning) {
-      const int w = x1 - x0, cnt = w * (y1 - y0);
+  int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
+  if (ntiles) tile_rect(px, py, radius, gx, gy, x0, y0, x1, y1);
+  const uint32_t dbits = __float_as_uint(depth);
+
+  if (exact_binning) {
+    uint32_t todo = __ballot_sync(FULL, ntiles != 0);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const int sx0 = __shfl_sync(FULL, x0, src), sy0 = __shfl_sync(FULL, y0, src);
+      const int w = __shfl_sync(FULL, x1, src) - sx0;
+      const int cnt = (int)__shfl_sync(FULL, ntiles, src);
+      const uint32_t soff = __shfl_sync(FULL, off, src), sdepth = __shfl_sync(FULL, dbits, src);
+      const uint32_t sid = (uint32_t)(warp_global * 32 + src);
       for (int t = lane; t < cnt; t += 32) {
-        const int y = y0 + t / w, x = x0 + t % w;
+        const int y = sy0 + t / w, x = sx0 + t % w;
         keys[soff + t] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | sdepth;
         vals[soff + t] = sid;
       }
-    } else {
-      const float sA = __shfl_sync(0xffffffffu, cA, src), sB = __shfl_sync(0xffffffffu, cB, src);
-      const float sC = __shfl_sync(0xffffffffu, cC, src), sop = __shfl_sync(0xffffffffu, op, src);
-      TileSpan span(spx, spy, sA, sB, sC, sop, x0, x1);
-      // rows are walked by all lanes together; each row's span is written by lanes 0..len-1 (len <= grid width)
-      uint32_t o = soff;
-      for (int ty = y0; ty < y1; ty++) {
-        int cx0, cx1;
-        span.row(ty, cx0, cx1);
-        const int len = cx1 - cx0;
-        for (int t = lane; t < len; t += 32) {
-          keys[o + t] = ((uint64_t)(uint32_t)(ty * gx + cx0 + t) << 32) | sdepth;
-          vals[o + t] = sid;
-        }
-        o += (uint32_t)len;
+    }
+    return;
+  }
+
+  // ---- culled list ----
+  const bool heavy = ntiles != 0 && (y1 - y0) > EMIT_HEAVY_ROWS;
+  if (ntiles != 0 && !heavy) {
+    TileSpan span(px, py, cA, cB, cC, op, x0, x1);
+    uint32_t o = off;
+    for (int ty = y0; ty < y1; ty++) {
+      int cx0, cx1;
+      span.row(ty, cx0, cx1);
+      for (int x = cx0; x < cx1; x++) {
+        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << 32) | dbits;
+        vals[o] = (uint32_t)i;
+        o++;
       }
+    }
+  }
+  uint32_t todo = __ballot_sync(FULL, heavy);
+  while (todo) {
+    const int src = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const float spx = __shfl_sync(FULL, px, src), spy = __shfl_sync(FULL, py, src);
+    const float sA = __shfl_sync(FULL, cA, src), sB = __shfl_sync(FULL, cB, src), sC = __shfl_sync(FULL, cC, src);
+    const float sop = __shfl_sync(FULL, op, src);
+    const int sx0 = __shfl_sync(FULL, x0, src), sx1 = __shfl_sync(FULL, x1, src);
+    const int sy0 = __shfl_sync(FULL, y0, src), sy1 = __shfl_sync(FULL, y1, src);
+    uint32_t base = __shfl_sync(FULL, off, src);
+    const uint32_t sdepth = __shfl_sync(FULL, dbits, src);
+    const uint32_t sid = (uint32_t)(warp_global * 32 + src);
+    TileSpan span(spx, spy, sA, sB, sC, sop, sx0, sx1);
+    for (int r0 = sy0; r0 < sy1; r0 += 32) {  // 32 rows at a time: lane = row
+      const int ty = r0 + lane;
+      int cx0 = 0, cx1 = 0;
+      if (ty < sy1) span.row(ty, cx0, cx1);
+      const int len = cx1 - cx0;
+      int incl = len;  // warp inclusive scan of the row lengths -> each row's offset
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int nb = __shfl_up_sync(FULL, incl, d);
+        if (lane >= d) incl += nb;
+      }
+      uint32_t o = base + (uint32_t)(incl - len);
+      for (int x = cx0; x < cx1; x++) {
+        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << 32) | sdepth;
+        vals[o] = sid;
+        o++;
+      }
+      base += (uint32_t)__shfl_sync(FULL, incl, 31);
     }
   }
 }
 
-void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const uint32_t* offsets, uint64_t* keys,
-                      uint32_t* vals, int exact_binning, cudaStream_t stream) {
+void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
+                      uint64_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, offsets, keys, vals, exact_binning);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, offsets, keys, vals, exact_binning);
   count_launch();
 }
 
@@ -339,6 +410,47 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint6
     }
   }
   if (idx == N - 1) ranges[cur].y = (uint32_t)N;
+}
+
+// Heaviest-first launch order of the tiles (longest-processing-time-first): the blend kernels walk one tile per
+// CTA and a tile's cost is proportional to its list length, so dispatching long lists first removes the tail where
+// a few SMs grind through 2000-deep lists while the rest idle.  Single CTA, counting sort into 64 length buckets.
+#define ORDER_NB 64
+__global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2* __restrict__ ranges,
+                                                          uint32_t* __restrict__ order,
+                                                          uint32_t* __restrict__ order_info, int heavy_fwd,
+                                                          int heavy_bwd) {
+  __shared__ uint32_t hist[ORDER_NB];
+  __shared__ uint32_t cursor[ORDER_NB];
+  if (threadIdx.x < ORDER_NB) hist[threadIdx.x] = 0;
+  __syncthreads();
+  auto bucket = [](uint2 r) -> int {
+    const uint32_t len = r.y - r.x;
+    return len == 0 ? ORDER_NB - 1 : (ORDER_NB - 2) - (int)min((uint32_t)(ORDER_NB - 2), len >> 5);
+  };
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&hist[bucket(ranges[t])], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    // a tile is "heavy" for a pass when its list has >= heavy_* splats (multiples of 32): prefix of the order
+    const int qf = min(ORDER_NB - 2, max(1, heavy_fwd >> 5)), qb = min(ORDER_NB - 2, max(1, heavy_bwd >> 5));
+    for (int b = 0; b < ORDER_NB; b++) {
+      cursor[b] = run;
+      run += hist[b];
+      if (b == (ORDER_NB - 2) - qf) order_info[0] = run;
+      if (b == (ORDER_NB - 2) - qb) order_info[1] = run;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) order[atomicAdd(&cursor[bucket(ranges[t])], 1u)] = (uint32_t)t;
+}
+
+void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream) {
+  if (tiles == 0) return;
+  static const int heavy_fwd = getenv("GAB200_HEAVY_FWD") ? atoi(getenv("GAB200_HEAVY_FWD")) : 32;
+  static const int heavy_bwd = getenv("GAB200_HEAVY_BWD") ? atoi(getenv("GAB200_HEAVY_BWD")) : 1024;
+  tile_order_kernel<<<1, 1024, 0, stream>>>(tiles, ranges, order, order_info, heavy_fwd, heavy_bwd);
+  count_launch();
 }
 
 void launch_tile_ranges(int64_t N, const uint64_t* keys, uint2* ranges, cudaStream_t stream) {

@@ -12,8 +12,9 @@
 namespace gab {
 
 template <bool BOUND>
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backward_args b, gab200_forward_args a,
+__global__ void __launch_bounds__(PRE_NT) preprocess_backward_kernel(gab200_backward_args b, gab200_forward_args a,
                                                                   const SplatRec* __restrict__ rec,
+                                                                  const SplatAux* __restrict__ aux,
                                                                   const uint8_t* __restrict__ clamped,
                                                                   const float* __restrict__ g2d) {
   __shared__ Camera cam;
@@ -24,18 +25,32 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backwar
     else if (t < 35) cam.campos[t - 32] = a.campos[t - 32];
     __syncthreads();
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.P) return;
-  const int W = a.image_width, H = a.image_height;
+  // SH coefficients in (for the view-direction term) and SH gradients out share one shared-memory tile:
+  // coalesced 128-bit global accesses, conflict-free (odd stride) per-thread row accesses.
+  __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   const int M = a.sh_coeffs;
-  const float4 q2 = rec[i].q2;
-  const int radius = __float_as_int(q2.z);
+  const int sh_width = BOUND ? 3 * (M - 1) : 3 * M;
+  const int sh_stride = sh_width | 1;
+  const int row0 = blockIdx.x * PRE_NT;
+  const int rows = min(PRE_NT, a.P - row0);
+  const float* sh_src = BOUND ? a.sh_rest : a.shs;
+  const bool stage_sh = a.colors_precomp == nullptr && sh_src != nullptr && sh_width > 0;
+  if (stage_sh) {
+    if (a.sh_degree > 0) stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, rows, sh_width, sh_stride);
+    __syncthreads();
+  }
+  float* my_sh = sh_s + threadIdx.x * sh_stride;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < a.P;
+  const int i = active ? idx : a.P - 1;
+  const int W = a.image_width, H = a.image_height;
+  const int radius = aux[i].radius;
 
   float gm[3] = {0.f, 0.f, 0.f}, gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   float gscale[3] = {0.f, 0.f, 0.f}, grot[4] = {0.f, 0.f, 0.f, 0.f};
   float g_op = 0.f, g2x = 0.f, g2y = 0.f, gcol[3] = {0.f, 0.f, 0.f};
   const bool use_sh = (a.colors_precomp == nullptr);
-  const bool visible = radius > 0;
+  const bool visible = active && radius > 0;
 
   Activated act;
   BindCtx ctx;
@@ -164,9 +179,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backwar
       const float x = d.x, y = d.y, z = d.z;
       float gd[3] = {0.f, 0.f, 0.f};
       if (a.sh_degree > 0) {
-        const float* sh = BOUND ? nullptr : a.shs + (size_t)i * M * 3;
-        const float* rest = BOUND ? a.sh_rest + (size_t)i * (M - 1) * 3 : nullptr;
-        auto SHV = [&](int k, int ch) -> float { return BOUND ? rest[3 * (k - 1) + ch] : sh[3 * k + ch]; };
+        auto SHV = [&](int k, int ch) -> float { return BOUND ? my_sh[3 * (k - 1) + ch] : my_sh[3 * k + ch]; };
 #pragma unroll
         for (int ch = 0; ch < 3; ch++) {
           float dxc = -SH_C1 * SHV(3, ch), dyc = -SH_C1 * SHV(1, ch), dzc = SH_C1 * SHV(2, ch);
@@ -201,27 +214,31 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backwar
         gm[2] += (-d0.x * d0.z * gd[0] - d0.y * d0.z * gd[1] + (s2 - d0.z * d0.z) * gd[2]) * inv3;
       }
     }
+    // this thread is done reading its own row: overwrite it with the gradient row, then the block writes it out
     if (BOUND) {
-      float* gdc = b.dL_dsh_dc + 3 * (size_t)i;
-      gdc[0] = B[0] * gRGB[0]; gdc[1] = B[0] * gRGB[1]; gdc[2] = B[0] * gRGB[2];
-      if (M > 1) {
-        float* gr = b.dL_dsh_rest + (size_t)i * (M - 1) * 3;
-        for (int k = 1; k < M; k++) {
-          const float bk = (k < nb) ? B[k] : 0.f;
-          gr[3 * (k - 1) + 0] = bk * gRGB[0];
-          gr[3 * (k - 1) + 1] = bk * gRGB[1];
-          gr[3 * (k - 1) + 2] = bk * gRGB[2];
-        }
+      if (active) {
+        float* gdc = b.dL_dsh_dc + 3 * (size_t)i;
+        gdc[0] = B[0] * gRGB[0]; gdc[1] = B[0] * gRGB[1]; gdc[2] = B[0] * gRGB[2];
       }
-    } else if (b.dL_dshs != nullptr) {
-      float* gs = b.dL_dshs + (size_t)i * M * 3;
+      for (int k = 1; k < M; k++) {
+        const float bk = (k < nb) ? B[k] : 0.f;
+        my_sh[3 * (k - 1) + 0] = bk * gRGB[0];
+        my_sh[3 * (k - 1) + 1] = bk * gRGB[1];
+        my_sh[3 * (k - 1) + 2] = bk * gRGB[2];
+      }
+    } else {
       for (int k = 0; k < M; k++) {
         const float bk = (k < nb) ? B[k] : 0.f;
-        gs[3 * k + 0] = bk * gRGB[0];
-        gs[3 * k + 1] = bk * gRGB[1];
-        gs[3 * k + 2] = bk * gRGB[2];
+        my_sh[3 * k + 0] = bk * gRGB[0];
+        my_sh[3 * k + 1] = bk * gRGB[1];
+        my_sh[3 * k + 2] = bk * gRGB[2];
       }
     }
+  }
+  if (stage_sh) {
+    __syncthreads();
+    float* dst = BOUND ? b.dL_dsh_rest : b.dL_dshs;
+    if (dst != nullptr) stage_rows_out<PRE_NT>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
   }
 
   // ---- Sigma -> (scale, rotation) [-> binding chain] ----
@@ -319,6 +336,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backwar
   }
 
   // ---- stores ----
+  if (!active) return;
   if (b.dL_dmeans3D != nullptr) {
     b.dL_dmeans3D[3 * (size_t)i + 0] = g_xyz[0];
     b.dL_dmeans3D[3 * (size_t)i + 1] = g_xyz[1];
@@ -349,15 +367,15 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(gab200_backwar
   }
 }
 
-void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const uint8_t* clamped,
-                                const float* g2d, cudaStream_t stream) {
+void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const SplatAux* aux,
+                                const uint8_t* clamped, const float* g2d, cudaStream_t stream) {
   const gab200_forward_args& a = *b.fwd;
-  const int threads = 256, blocks = (a.P + threads - 1) / threads;
+  const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_backward_kernel<true><<<blocks, threads, 0, stream>>>(b, a, rec, clamped, g2d);
+    preprocess_backward_kernel<true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
   else
-    preprocess_backward_kernel<false><<<blocks, threads, 0, stream>>>(b, a, rec, clamped, g2d);
+    preprocess_backward_kernel<false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
   count_launch();
 }
 

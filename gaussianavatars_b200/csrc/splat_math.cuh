@@ -6,6 +6,57 @@
 
 namespace gab {
 
+#define PRE_NT 128                 // threads per block of the per-splat kernels
+#define SH_SMEM_STRIDE_MAX 49      // 16 coefficients * 3 channels, padded to an odd stride
+
+// Cooperative copy of rows [row0, row0+rows) of a row-major [*, width] float matrix into shared memory with row
+// stride `pstride` (odd -> the later per-thread row reads are bank-conflict free).  Global side: 128-bit loads.
+template <int NT>
+__device__ __forceinline__ void stage_rows_in(float* smem, const float* __restrict__ g, size_t row0, int rows, int width,
+                                              int pstride) {
+  const float* src = g + row0 * (size_t)width;
+  const int total = rows * width;
+  const int nvec = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? total / 4 : 0;
+  for (int v = threadIdx.x; v < nvec; v += NT) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(src) + v);
+    const int g0 = 4 * v;
+    int r = g0 / width, e = g0 - r * width;
+    const float vals[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      smem[r * pstride + e] = vals[k];
+      if (++e == width) { e = 0; ++r; }
+    }
+  }
+  for (int q = nvec * 4 + threadIdx.x; q < total; q += NT) {
+    const int r = q / width;
+    smem[r * pstride + (q - r * width)] = src[q];
+  }
+}
+// The reverse: rows staged in shared memory -> global, 128-bit stores.
+template <int NT>
+__device__ __forceinline__ void stage_rows_out(const float* smem, float* __restrict__ g, size_t row0, int rows,
+                                               int width, int pstride) {
+  float* dst = g + row0 * (size_t)width;
+  const int total = rows * width;
+  const int nvec = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? total / 4 : 0;
+  for (int v = threadIdx.x; v < nvec; v += NT) {
+    const int g0 = 4 * v;
+    int r = g0 / width, e = g0 - r * width;
+    float vals[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      vals[k] = smem[r * pstride + e];
+      if (++e == width) { e = 0; ++r; }
+    }
+    reinterpret_cast<float4*>(dst)[v] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+  }
+  for (int q = nvec * 4 + threadIdx.x; q < total; q += NT) {
+    const int r = q / width;
+    dst[q] = smem[r * pstride + (q - r * width)];
+  }
+}
+
 __device__ __forceinline__ float3 xform4x3(const float* M, float3 p) {
   float3 r;
   r.x = M[0] * p.x + M[4] * p.y + M[8] * p.z + M[12];

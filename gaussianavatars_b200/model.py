@@ -84,15 +84,29 @@ class MeshBoundGaussians:
         self.verts_rest = None if verts is None else verts.to(device)
         self.faces = None if faces is None else faces.to(device)
         self.pose_fn = pose_fn
-        self.face_center = self.face_orien_mat = self.face_scaling = self.face_orien_quat = None
+        self.faces_i32 = None if faces is None else self.faces.to(torch.int32).contiguous()
+        self.face_center = self.face_orien_mat = self.face_scaling = self._face_orien_quat = None
         self.verts = None
         self.timestep = None
 
     # ---- mesh ----
     def update_mesh_properties(self, verts: torch.Tensor):
+        """scene/flame_gaussian_model.py:137-147.  On the GPU the frame is ONE library launch; the quaternion form is
+        only materialised if the eager reference route asks for it (the fused route composes matrices)."""
         self.verts = verts
-        self.face_center, self.face_orien_mat, self.face_scaling = face_frame(verts, self.faces)
-        self.face_orien_quat = rotmat_to_quat_wxyz(self.face_orien_mat)
+        if verts.is_cuda:
+            from .rasterizer import face_frame as face_frame_cuda
+
+            self.face_center, self.face_orien_mat, self.face_scaling = face_frame_cuda(verts, self.faces_i32)
+        else:
+            self.face_center, self.face_orien_mat, self.face_scaling = face_frame(verts, self.faces)
+        self._face_orien_quat = None
+
+    @property
+    def face_orien_quat(self):
+        if self._face_orien_quat is None and self.face_orien_mat is not None:
+            self._face_orien_quat = rotmat_to_quat_wxyz(self.face_orien_mat)
+        return self._face_orien_quat
 
     def select_mesh_by_timestep(self, timestep: int):
         self.timestep = timestep

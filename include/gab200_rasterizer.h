@@ -164,6 +164,16 @@ int32_t gab200_mark_visible(int32_t P, const float* means3D, const float* viewma
 int32_t gab200_bind_activate(const gab200_forward_args* args, float* means3D, float* opacities, float* scales,
                              float* cov3D, void* stream);
 
+/* Per-face frame of the posed mesh in one launch.  Replaces FlameGaussianModel.update_mesh_properties +
+ * compute_face_orientation (scene/flame_gaussian_model.py:137-147, utils/graphics_utils.py:116-135):
+ * verts [V,3], faces [F,3] int32 -> face_center [F,3], face_orien_mat [F,3,3] (columns a0 a1 a2), face_scaling [F]. */
+int32_t gab200_face_frame_forward(int32_t F, int32_t V, const float* verts, const int32_t* faces, float* face_center,
+                                  float* face_orien_mat, float* face_scaling, void* stream);
+/* Its backward: dL/dverts [V,3] (zeroed by the library, then accumulated).  Any upstream gradient may be NULL (= 0). */
+int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, const int32_t* faces,
+                                   const float* dL_dface_center, const float* dL_dface_orien_mat,
+                                   const float* dL_dface_scaling, float* dL_dverts, void* stream);
+
 /* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
  * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */
 int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,

