@@ -307,6 +307,7 @@ def main():
     K = args.steps
     N.stage_timing(True)
     N.stage_times(reset=True)
+    N.host_times(reset=True)
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     launches0 = N.launch_count()
@@ -323,6 +324,7 @@ def main():
     launches = N.launch_count() - launches0
     stage = N.stage_times(reset=True)
     N.stage_timing(False)
+    host_us = N.host_times(reset=True)
     ms_steps = [s.elapsed_time(e) for s, e in zip(starts, ends)]
     ms_total = sum(ms_steps)
 
@@ -400,6 +402,7 @@ def main():
                                "achieved_gbs": frame_alg / ((ms_total / K) * 1e-3) / 1e9,
                                "frac": frame_alg / ((ms_total / K) * 1e-3) / 1e9 / peak}},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "host_us_in_forward": {k: round(v, 1) for k, v in host_us.items()},
         "wall_s_timed_region": wall1 - wall0,
     }
     if world == 1 and not args.no_cpu_baseline:

@@ -26,7 +26,8 @@ class ForwardArgs(C.Structure):
         ("abi_version", C.c_uint32), ("input_mode", C.c_int32), ("P", C.c_int32), ("sh_degree", C.c_int32),
         ("sh_coeffs", C.c_int32), ("image_width", C.c_int32), ("image_height", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
-        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_backward", C.c_int32), ("exact_binning", C.c_int32),
+        ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_backward", C.c_int32), ("binning_hint", C.c_int32),
+        ("exact_binning", C.c_int32),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
         ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
         ("cov3D_precomp", C.c_void_p), ("shs", C.c_void_p), ("sh_dc", C.c_void_p), ("sh_rest", C.c_void_p),
@@ -43,7 +44,8 @@ class FrameState(C.Structure):
         ("num_rendered", C.c_int64), ("num_candidates", C.c_int64),
         ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("image_buffer", C.c_void_p),
         ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t), ("image_bytes", C.c_size_t),
-        ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32),
+        ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32), ("depth_bits", C.c_int32),
+        ("depth_prefix", C.c_uint32),
     ]
 
 
@@ -61,7 +63,7 @@ class BackwardArgs(C.Structure):
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
-                    "gab200_face_frame_backward")
+                    "gab200_face_frame_backward", "gab200_host_times")
 
 _lib = None
 _lock = threading.Lock()
@@ -103,6 +105,8 @@ def lib():
         L.gab200_export_binning.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
         L.gab200_launch_count.restype = C.c_int64
+        L.gab200_host_times.restype = None
+        L.gab200_host_times.argtypes = [C.POINTER(C.c_double), C.c_int32]
         L.gab200_face_frame_forward.restype = C.c_int32
         L.gab200_face_frame_forward.argtypes = [C.c_int32, C.c_int32] + [C.c_void_p] * 6
         L.gab200_face_frame_backward.restype = C.c_int32
@@ -140,6 +144,15 @@ def stage_times(reset: bool = True):
     n = (C.c_int64 * len(STAGES))()
     check(lib().gab200_stage_times(ms, n, int(reset)), "gab200_stage_times")
     return {s: (ms[i], n[i]) for i, s in enumerate(STAGES)}
+
+
+def host_times(reset: bool = True):
+    """Host-side microseconds inside gab200_forward since the last reset (see the header)."""
+    out = (C.c_double * 6)()
+    lib().gab200_host_times(out, int(reset))
+    n = max(out[5], 1.0)
+    keys = ("pre_sync_launch", "wait_N", "binning_alloc", "emit_sort_dispatch", "blend_dispatch")
+    return {k: out[i] / n for i, k in enumerate(keys)}
 
 
 def launch_count() -> int:

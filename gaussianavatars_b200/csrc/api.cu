@@ -2,6 +2,7 @@
 // validation, carving of the three caller-allocated byte buffers, stage launches, the single host sync that sizes
 // the binning buffer.  No torch types, no exceptions, no global state beyond a launch counter.
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -20,6 +21,7 @@ struct GeomView {
   uint32_t* tiles_touched;
   uint32_t* offsets;
   uint8_t* clamped;
+  uint32_t* depth_range;  // [0] = min depth bits, [1] = ~max depth bits over the emitting splats
   float* g2d;
   void* scan_temp;
   size_t scan_temp_bytes;
@@ -33,12 +35,31 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   g.tiles_touched = c.take<uint32_t>((size_t)P);
   g.offsets = c.take<uint32_t>((size_t)P);
   g.clamped = c.take<uint8_t>((size_t)P);
+  g.depth_range = c.take<uint32_t>(4);
   g.g2d = need_backward ? c.take<float>((size_t)P * GAB_G2D_STRIDE) : nullptr;
   g.scan_temp_bytes = scan_temp_bytes(P);
   g.scan_temp = c.take<char>(g.scan_temp_bytes);
   g.bytes = c.bytes();
   return g;
 }
+// cub's temp-storage queries run its whole host-side dispatch; the answer only grows with N -> cache it.
+struct SortTempCache {
+  int64_t n = -1;
+  int bits = -1;
+  size_t bytes = 0;
+};
+static thread_local SortTempCache t_sort_cache;
+static size_t cached_sort_temp_bytes(int64_t N, int bits) {
+  SortTempCache& c = t_sort_cache;
+  if (c.bits != bits || N > c.n) {
+    const int64_t n_up = N + N / 2 + 1024;  // headroom so that the query is rare
+    c.bytes = sort_temp_bytes(n_up, bits);
+    c.n = n_up;
+    c.bits = bits;
+  }
+  return c.bytes;
+}
+
 struct BinView {
   uint64_t* keys[2];
   uint32_t* vals[2];
@@ -56,7 +77,8 @@ static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_bac
   b.vals[0] = c.take<uint32_t>(n);
   b.vals[1] = c.take<uint32_t>(n);
   b.strip_mask = need_backward ? c.take<uint8_t>(n) : nullptr;
-  b.sort_temp_bytes = sort_temp_bytes(N > 0 ? N : 1, sort_bits);
+  (void)sort_bits;
+  b.sort_temp_bytes = cached_sort_temp_bytes(N > 0 ? N : 1, 64);  // upper bound over every key width we may use
   b.sort_temp = c.take<char>(b.sort_temp_bytes);
   b.bytes = c.bytes();
   return b;
@@ -114,6 +136,26 @@ struct StageScope {
     }
   }
 };
+
+static double g_host_us[6] = {0, 0, 0, 0, 0, 0};
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// N is read back through a pinned slot + event spin: lower wake-up latency than cudaStreamSynchronize and it only
+// waits for the copy, not for anything the caller may have queued behind it on other streams.
+struct PinnedSlot {
+  uint32_t* host = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool ok() {
+    if (host == nullptr) {
+      if (cudaHostAlloc((void**)&host, 64, cudaHostAllocDefault) != cudaSuccess) return false;
+      if (cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) return false;
+    }
+    return true;
+  }
+};
+static thread_local PinnedSlot t_slot;
 
 static int check_arch() {
   static std::atomic<int> cached{0};  // 0 unknown, 1 ok, -1 bad
@@ -199,6 +241,13 @@ int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[
 }
 int64_t gab200_launch_count(void) { return g_launches.load(); }
 
+void gab200_host_times(double out[6], int32_t reset) {
+  for (int i = 0; i < 6; i++) {
+    if (out) out[i] = g_host_us[i];
+    if (reset) g_host_us[i] = 0;
+  }
+}
+
 const char* gab200_status_string(int32_t s) {
   switch (s) {
     case GAB200_OK: return "ok";
@@ -233,12 +282,19 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   st->geom_buffer = geom; st->geom_bytes = g.bytes;
   st->image_buffer = img; st->image_bytes = iv.bytes;
   st->sort_bits = 32 + (int)tile_bits((uint32_t)(gx * gy));
+  st->depth_bits = 32;
+  st->depth_prefix = 0;
 
   int64_t N = 0;
+  const double t0 = now_us();
+  double t_sync0 = t0, t_sync1 = t0;
+  void* bin = nullptr;
+  size_t bin_bytes_have = 0;
   if (P > 0) {
     {
       StageScope sc(GAB200_STAGE_PREPROCESS, stream);
-      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, stream);
+      GAB_CUDA(cudaMemsetAsync(g.depth_range, 0xff, 2 * sizeof(uint32_t), stream));
+      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_range, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
@@ -246,17 +302,46 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
       GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.offsets, P, stream));
     }
     GAB_STAGE_CHECK(dbg, stream);
-    uint32_t n_host = 0;
-    GAB_CUDA(cudaMemcpyAsync(&n_host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    GAB_CUDA(cudaStreamSynchronize(stream));
-    N = (int64_t)n_host;
+    if (!t_slot.ok()) return GAB200_ERR_CUDA;
+    GAB_CUDA(cudaMemcpyAsync(t_slot.host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GAB_CUDA(cudaMemcpyAsync(t_slot.host + 1, g.depth_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
+    // speculative binning allocation while the GPU is still busy with preprocess + scan
+    t_sync0 = now_us();
+    if (a->binning_hint > 0) {
+      bin_bytes_have = carve_binning(nullptr, a->binning_hint, st->sort_bits, nb).bytes;
+      bin = a->alloc_binning(a->alloc_user, bin_bytes_have);
+      if (bin == nullptr) return GAB200_ERR_ALLOC;
+    }
+    const double t_alloc = now_us();
+    g_host_us[2] += t_alloc - t_sync0;
+    t_sync0 = t_alloc;
+    for (;;) {
+      const cudaError_t q = cudaEventQuery(t_slot.ev);
+      if (q == cudaSuccess) break;
+      if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
+    }
+    N = (int64_t)t_slot.host[0];
+    if (N > 0) {
+      const uint32_t dmin = t_slot.host[1], dmax = ~t_slot.host[2];
+      const uint32_t diff = dmin ^ dmax;
+      int db = 1;
+      while (db < 32 && (diff >> db) != 0) db++;
+      st->depth_bits = db;
+      st->depth_prefix = db >= 32 ? 0u : (dmin & ~((1u << db) - 1u));
+      st->sort_bits = db + (int)tile_bits((uint32_t)(gx * gy));
+    }
+    t_sync1 = now_us();
   }
   st->num_rendered = N;
   st->num_candidates = N;
 
   BinView bsz = carve_binning(nullptr, N, st->sort_bits, nb);
-  void* bin = a->alloc_binning(a->alloc_user, bsz.bytes);
-  if (bin == nullptr) return GAB200_ERR_ALLOC;
+  if (bin == nullptr || bsz.bytes > bin_bytes_have) {
+    bin = a->alloc_binning(a->alloc_user, bsz.bytes);
+    if (bin == nullptr) return GAB200_ERR_ALLOC;
+  }
+  const double t_alloc2 = now_us();
   BinView bv = carve_binning(bin, N, st->sort_bits, nb);
   st->binning_buffer = bin; st->binning_bytes = bv.bytes;
 
@@ -266,7 +351,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (N > 0) {
     {
       StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, st->depth_bits, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
@@ -277,7 +362,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     GAB_STAGE_CHECK(dbg, stream);
     {
       StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-      launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
+      launch_tile_ranges(N, bv.keys[selector], st->depth_bits, iv.ranges, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
   }
@@ -286,12 +371,20 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
     launch_tile_order(gx * gy, iv.ranges, iv.order, iv.order_info, stream);
   }
+  const double t_binned = now_us();
   {
     StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
     launch_blend_forward(W, H, iv.ranges, iv.order, iv.order_info, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
                          bv.strip_mask, stream);
   }
   GAB_STAGE_CHECK(dbg, stream);
+  const double t_end = now_us();
+  g_host_us[0] += t_sync0 - t0 - 0.0;
+  g_host_us[1] += t_sync1 - t_sync0;
+  g_host_us[2] += t_alloc2 - t_sync1;
+  g_host_us[3] += t_binned - t_alloc2;
+  g_host_us[4] += t_end - t_binned;
+  g_host_us[5] += 1;
   return N;
 }
 
@@ -389,7 +482,7 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
   BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, a->need_backward != 0);
   ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
   const size_t N = (size_t)st->num_rendered;
-  if (keys && N) GAB_CUDA(cudaMemcpyAsync(keys, bv.keys[st->sorted_selector], 8 * N, cudaMemcpyDeviceToDevice, stream));
+  if (keys && N) launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], st->depth_bits, st->depth_prefix, keys, stream);
   if (values && N) GAB_CUDA(cudaMemcpyAsync(values, bv.vals[st->sorted_selector], 4 * N, cudaMemcpyDeviceToDevice, stream));
   if (ranges) GAB_CUDA(cudaMemcpyAsync(ranges, iv.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));
   return GAB200_OK;

@@ -70,13 +70,15 @@ struct TileSpan {
 
 // ---- launchers (each counts its launches) ----
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, cudaStream_t stream);
+                       uint8_t* clamped, uint32_t* depth_range, cudaStream_t stream);
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
-                      uint64_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
-void launch_tile_ranges(int64_t N, const uint64_t* keys, uint2* ranges, cudaStream_t stream);
+                      uint64_t* keys, uint32_t* vals, int exact_binning, int depth_bits, cudaStream_t stream);
+void launch_tile_ranges(int64_t N, const uint64_t* keys, int depth_bits, uint2* ranges, cudaStream_t stream);
+void launch_expand_keys(int64_t N, const uint64_t* keys, int depth_bits, uint32_t depth_prefix, uint64_t* out,
+                        cudaStream_t stream);
 void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream);
 
 // binning.cu (cub)

@@ -33,7 +33,8 @@ template <bool BOUND>
 __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args a, SplatRec* __restrict__ rec,
                                                             SplatAux* __restrict__ aux,
                                                             uint32_t* __restrict__ tiles_touched,
-                                                            uint8_t* __restrict__ clamped, int exact_binning) {
+                                                            uint8_t* __restrict__ clamped,
+                                                            uint32_t* __restrict__ depth_range, int exact_binning) {
   __shared__ Camera cam;
   __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   stage_camera(a, cam);
@@ -47,9 +48,12 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, min(PRE_NT, a.P - row0), sh_width, sh_stride);
     __syncthreads();
   }
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.P) return;
-  const float* my_sh = sh_s + threadIdx.x * sh_stride;
+  // lanes past the end redo splat P-1 with all writes suppressed, so that every warp reaches the warp-wide
+  // depth-range reduction below with all 32 lanes
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool active = idx < a.P;
+  const int i = active ? idx : a.P - 1;
+  const float* my_sh = sh_s + (active ? threadIdx.x : (a.P - 1 - blockIdx.x * PRE_NT)) * sh_stride;
   const int W = a.image_width, H = a.image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
 
@@ -202,6 +206,18 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
       }
     }
   }
+  {
+    // range of the depth bit patterns over the splats that emit instances: the sort only needs the bits that vary
+    const uint32_t db = __float_as_uint(depth_out);
+    const bool emits = active && tiles_out != 0;
+    const uint32_t lo = __reduce_min_sync(0xffffffffu, emits ? db : 0xffffffffu);
+    const uint32_t hi_inv = __reduce_min_sync(0xffffffffu, emits ? ~db : 0xffffffffu);
+    if ((threadIdx.x & 31) == 0 && lo != 0xffffffffu) {
+      atomicMin(depth_range, lo);
+      atomicMin(depth_range + 1, hi_inv);
+    }
+  }
+  if (!active) return;
   rec[i] = out;
   SplatAux ax;
   ax.depth = depth_out; ax.radius = radius_out; ax.tiles = tiles_out; ax.pad = 0;
@@ -212,13 +228,13 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
 }
 
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, cudaStream_t stream) {
+                       uint8_t* clamped, uint32_t* depth_range, cudaStream_t stream) {
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, a.exact_binning);
+    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_range, a.exact_binning);
   else
-    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, a.exact_binning);
+    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_range, a.exact_binning);
   count_launch();
 }
 
@@ -289,7 +305,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
                                                         const SplatAux* __restrict__ aux,
                                                         const uint32_t* __restrict__ offsets,
                                                         uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        int exact_binning) {
+                                                        int exact_binning, int depth_bits) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -312,7 +328,9 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   }
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   if (ntiles) tile_rect(px, py, radius, gx, gy, x0, y0, x1, y1);
-  const uint32_t dbits = __float_as_uint(depth);
+  // key = tile << depth_bits | (low depth_bits bits of the fp32 depth): the dropped high bits are identical for
+  // every emitting splat of this frame, so ascending key order == ascending (tile << 32 | depth) order
+  const uint32_t dbits = depth_bits >= 32 ? __float_as_uint(depth) : (__float_as_uint(depth) & ((1u << depth_bits) - 1u));
 
   if (exact_binning) {
     uint32_t todo = __ballot_sync(FULL, ntiles != 0);
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const uint32_t sid = (uint32_t)(warp_global * 32 + src);
       for (int t = lane; t < cnt; t += 32) {
         const int y = sy0 + t / w, x = sx0 + t % w;
-        keys[soff + t] = ((uint64_t)(uint32_t)(y * gx + x) << 32) | sdepth;
+        keys[soff + t] = ((uint64_t)(uint32_t)(y * gx + x) << depth_bits) | sdepth;
         vals[soff + t] = sid;
       }
     }
@@ -342,7 +360,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       int cx0, cx1;
       span.row(ty, cx0, cx1);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << 32) | dbits;
+        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << depth_bits) | dbits;
         vals[o] = (uint32_t)i;
         o++;
       }
@@ -374,7 +392,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       }
       uint32_t o = base + (uint32_t)(incl - len);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << 32) | sdepth;
+        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << depth_bits) | sdepth;
         vals[o] = sid;
         o++;
       }
@@ -384,11 +402,11 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
 }
 
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
-                      uint64_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
+                      uint64_t* keys, uint32_t* vals, int exact_binning, int depth_bits, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, offsets, keys, vals, exact_binning);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, offsets, keys, vals, exact_binning, depth_bits);
   count_launch();
 }
 
@@ -396,14 +414,14 @@ void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux
 // K5: tile ranges from key transitions in the sorted stream (ranges pre-zeroed by the caller).
 // =====================================================================================================
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint64_t* __restrict__ keys,
-                                                          uint2* __restrict__ ranges) {
+                                                          int depth_bits, uint2* __restrict__ ranges) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
-  const uint32_t cur = (uint32_t)(keys[idx] >> 32);
+  const uint32_t cur = (uint32_t)(keys[idx] >> depth_bits);
   if (idx == 0)
     ranges[cur].x = 0;
   else {
-    const uint32_t prev = (uint32_t)(keys[idx - 1] >> 32);
+    const uint32_t prev = (uint32_t)(keys[idx - 1] >> depth_bits);
     if (cur != prev) {
       ranges[prev].y = (uint32_t)idx;
       ranges[cur].x = (uint32_t)idx;
@@ -428,7 +446,16 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2
     const uint32_t len = r.y - r.x;
     return len == 0 ? ORDER_NB - 1 : (ORDER_NB - 2) - (int)min((uint32_t)(ORDER_NB - 2), len >> 5);
   };
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&hist[bucket(ranges[t])], 1u);
+  // warp-aggregated counting sort (most tiles share a few buckets -- e.g. "empty" -- so per-thread shared-memory
+  // atomics would serialise): lanes with equal buckets elect a leader that adds the group's size once
+  const int lane = threadIdx.x & 31;
+  const int rounds = (tiles + blockDim.x - 1) / blockDim.x;
+  for (int r = 0; r < rounds; r++) {
+    const int t = r * blockDim.x + threadIdx.x;
+    const int b = t < tiles ? bucket(ranges[t]) : ORDER_NB;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    if (t < tiles && lane == __ffs(peers) - 1) atomicAdd(&hist[b], (uint32_t)__popc(peers));
+  }
   __syncthreads();
   if (threadIdx.x == 0) {
     uint32_t run = 0;
@@ -442,7 +469,16 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) order[atomicAdd(&cursor[bucket(ranges[t])], 1u)] = (uint32_t)t;
+  for (int r = 0; r < rounds; r++) {
+    const int t = r * blockDim.x + threadIdx.x;
+    const int b = t < tiles ? bucket(ranges[t]) : ORDER_NB;
+    const unsigned peers = __match_any_sync(0xffffffffu, b);
+    const int leader = __ffs(peers) - 1;
+    uint32_t base = 0;
+    if (t < tiles && lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (t < tiles) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)t;
+  }
 }
 
 void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream) {
@@ -453,11 +489,27 @@ void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t
   count_launch();
 }
 
-void launch_tile_ranges(int64_t N, const uint64_t* keys, uint2* ranges, cudaStream_t stream) {
+__global__ void expand_keys_kernel(int64_t N, const uint64_t* __restrict__ keys, int depth_bits, uint32_t prefix,
+                                   uint64_t* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const uint64_t k = keys[i];
+  const uint64_t low = depth_bits >= 32 ? (k & 0xffffffffull) : (k & ((1ull << depth_bits) - 1ull));
+  out[i] = ((k >> depth_bits) << 32) | (uint64_t)prefix | low;
+}
+// the reference's key format (tile << 32 | fp32 depth bits) from the compact sort keys (parity export)
+void launch_expand_keys(int64_t N, const uint64_t* keys, int depth_bits, uint32_t depth_prefix, uint64_t* out,
+                        cudaStream_t stream) {
+  if (N == 0) return;
+  expand_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, keys, depth_bits, depth_prefix, out);
+  count_launch();
+}
+
+void launch_tile_ranges(int64_t N, const uint64_t* keys, int depth_bits, uint2* ranges, cudaStream_t stream) {
   if (N == 0) return;
   const int threads = 256;
   const int64_t blocks = (N + threads - 1) / threads;
-  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, keys, ranges);
+  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, keys, depth_bits, ranges);
   count_launch();
 }
 

@@ -78,6 +78,7 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
     a.debug = int(bool(rs.debug))
     a.need_backward = int(need_backward)
     a.exact_binning = int(_EXACT_BINNING)
+    a.binning_hint = _binning_hint.get((device, a.image_width, a.image_height, P), 0)
     cams = (_cam(rs.bg, "bg", device), _cam(rs.viewmatrix, "viewmatrix", device),
             _cam(rs.projmatrix, "projmatrix", device), _cam(rs.campos, "campos", device))
     a.bg, a.viewmatrix, a.projmatrix, a.campos = (t.data_ptr() for t in cams)
@@ -86,6 +87,7 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
 
 _KEEP_LAST = False
 _last = None
+_binning_hint = {}  # (device, W, H, P) -> expected instance count (last N * 1.25): see gab200_forward_args.binning_hint
 
 
 def keep_last_state(flag: bool):
@@ -125,6 +127,7 @@ def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
         stream = torch.cuda.current_stream(device).cuda_stream
         n = N.lib().gab200_forward(C.byref(a), C.byref(st), C.c_void_p(stream))
     N.check(n, "gab200_forward")
+    _binning_hint[(device, a.image_width, a.image_height, P)] = min(int(n * 1.25) + 4096, 2**31 - 1)
     if _KEEP_LAST:
         global _last
         # pooled (inference) scratch stays valid until the next no_grad forward on this device

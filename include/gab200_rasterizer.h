@@ -68,6 +68,9 @@ typedef struct gab200_forward_args {
   int32_t prefiltered;     /* accepted for signature parity; the near-plane cull is always applied */
   int32_t debug;           /* 1: synchronise + check after every stage (reference `debug=` flag) */
   int32_t need_backward;   /* 0: inference -- per-pixel state for backward is not written */
+  int32_t binning_hint;    /* expected number of (splat,tile) instances (0 = unknown), e.g. last frame's N * 1.25: the
+                              binning buffer is then requested BEFORE the host sync that reads N back, taking the
+                              allocation off the critical path; it is requested again only if N exceeds the hint */
   int32_t exact_binning;   /* 1: emit the reference's full 3-sigma bounding-square instance list;
                               0: additionally drop (splat,tile) pairs that provably contribute nothing
                                  (alpha < 1/255 over the whole tile): image/gradients unchanged */
@@ -115,7 +118,11 @@ typedef struct gab200_frame_state {
   void* image_buffer;
   size_t geom_bytes, binning_bytes, image_bytes;
   int32_t sorted_selector;    /* which half of the sort double-buffer holds the sorted stream */
-  int32_t sort_bits;          /* radix-sort key width used: 32 + bits(tile id) */
+  int32_t sort_bits;          /* radix-sort key width used: depth_bits + bits(tile id)  (<= 32 + bits(tile id)) */
+  int32_t depth_bits;         /* the sort keys carry only the low depth_bits bits of the fp32 depth pattern: all visible
+                                 splats of the frame share the higher bits (depth_prefix), so the order is the same as
+                                 sorting the reference's full (tile << 32 | depth) key */
+  uint32_t depth_prefix;
 } gab200_frame_state;
 
 /* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
@@ -194,6 +201,10 @@ enum {
   GAB200_NUM_STAGES = 8
 };
 void gab200_stage_timing_enable(int32_t enable);
+/* Host-side wall time (microseconds, accumulated since the last reset) spent inside gab200_forward, split into
+ * [0] launches before the sync, [1] waiting for N, [2] binning allocation callback(s), [3] emit+sort+ranges dispatch,
+ * [4] blend dispatch, [5] number of forwards.  Profiling aid; always on (a few clock reads per call). */
+void gab200_host_times(double out[6], int32_t reset);
 int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[GAB200_NUM_STAGES], int32_t reset);
 
 /* Number of kernels launched by this library on the calling process so far (bench.py's gpu_launches claim). */
