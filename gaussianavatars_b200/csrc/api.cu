@@ -15,13 +15,34 @@ namespace gab {
 static std::atomic<int64_t> g_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// cub's temp-storage queries run its whole host-side dispatch; the answer only grows with N -> cache it.
+struct SortTempCache {
+  int64_t n = -1;
+  int bits = -1;
+  size_t bytes = 0;
+};
+static thread_local SortTempCache t_sort_cache[2];  // [0]: stage A (32-bit depth keys), [1]: stage B (tile ids)
+static size_t cached_sort_temp_bytes(int64_t N, int bits) {
+  SortTempCache& c = t_sort_cache[bits == 32 ? 0 : 1];
+  if (c.bits != bits || N > c.n) {
+    const int64_t n_up = N + N / 2 + 1024;  // headroom so that the query is rare
+    c.bytes = sort_temp_bytes(n_up, bits);
+    c.n = n_up;
+    c.bits = bits;
+  }
+  return c.bytes;
+}
+
 struct GeomView {
   SplatRec* rec;
   SplatAux* aux;
   uint32_t* tiles_touched;
   uint32_t* offsets;
   uint8_t* clamped;
-  uint32_t* depth_range;  // [0] = min depth bits, [1] = ~max depth bits over the emitting splats
+  uint32_t* depth_keys[2];  // stage-A sort: fp32 depth bit patterns (double buffer)
+  uint32_t* ids[2];         //               splat ids (double buffer) -> depth order
+  void* sortA_temp;
+  size_t sortA_temp_bytes;
   float* g2d;
   void* scan_temp;
   size_t scan_temp_bytes;
@@ -35,34 +56,21 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   g.tiles_touched = c.take<uint32_t>((size_t)P);
   g.offsets = c.take<uint32_t>((size_t)P);
   g.clamped = c.take<uint8_t>((size_t)P);
-  g.depth_range = c.take<uint32_t>(4);
+  g.depth_keys[0] = c.take<uint32_t>((size_t)P);
+  g.depth_keys[1] = c.take<uint32_t>((size_t)P);
+  g.ids[0] = c.take<uint32_t>((size_t)P);
+  g.ids[1] = c.take<uint32_t>((size_t)P);
+  g.sortA_temp_bytes = cached_sort_temp_bytes(P > 0 ? P : 1, 32);
+  g.sortA_temp = c.take<char>(g.sortA_temp_bytes);
   g.g2d = need_backward ? c.take<float>((size_t)P * GAB_G2D_STRIDE) : nullptr;
   g.scan_temp_bytes = scan_temp_bytes(P);
   g.scan_temp = c.take<char>(g.scan_temp_bytes);
   g.bytes = c.bytes();
   return g;
 }
-// cub's temp-storage queries run its whole host-side dispatch; the answer only grows with N -> cache it.
-struct SortTempCache {
-  int64_t n = -1;
-  int bits = -1;
-  size_t bytes = 0;
-};
-static thread_local SortTempCache t_sort_cache;
-static size_t cached_sort_temp_bytes(int64_t N, int bits) {
-  SortTempCache& c = t_sort_cache;
-  if (c.bits != bits || N > c.n) {
-    const int64_t n_up = N + N / 2 + 1024;  // headroom so that the query is rare
-    c.bytes = sort_temp_bytes(n_up, bits);
-    c.n = n_up;
-    c.bits = bits;
-  }
-  return c.bytes;
-}
-
 struct BinView {
-  uint64_t* keys[2];
-  uint32_t* vals[2];
+  uint32_t* keys[2];  // tile ids (stage-B sort keys)
+  uint32_t* vals[2];  // splat ids
   uint8_t* strip_mask;  // per sorted instance: which 16x2 pixel strips of its tile it contributed to (forward -> backward)
   void* sort_temp;
   size_t sort_temp_bytes;
@@ -72,13 +80,12 @@ static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_bac
   BinView b;
   Carver c(base);
   const size_t n = (size_t)(N > 0 ? N : 1);
-  b.keys[0] = c.take<uint64_t>(n);
-  b.keys[1] = c.take<uint64_t>(n);
+  b.keys[0] = c.take<uint32_t>(n);
+  b.keys[1] = c.take<uint32_t>(n);
   b.vals[0] = c.take<uint32_t>(n);
   b.vals[1] = c.take<uint32_t>(n);
   b.strip_mask = need_backward ? c.take<uint8_t>(n) : nullptr;
-  (void)sort_bits;
-  b.sort_temp_bytes = cached_sort_temp_bytes(N > 0 ? N : 1, 64);  // upper bound over every key width we may use
+  b.sort_temp_bytes = cached_sort_temp_bytes(N > 0 ? N : 1, sort_bits);
   b.sort_temp = c.take<char>(b.sort_temp_bytes);
   b.bytes = c.bytes();
   return b;
@@ -281,9 +288,10 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   ImageView iv = carve_image(img, W, H, nb);
   st->geom_buffer = geom; st->geom_bytes = g.bytes;
   st->image_buffer = img; st->image_bytes = iv.bytes;
-  st->sort_bits = 32 + (int)tile_bits((uint32_t)(gx * gy));
-  st->depth_bits = 32;
+  st->sort_bits = (int)tile_bits((uint32_t)(gx * gy));  // stage B: tile id only
+  st->depth_bits = 32;                                  // stage A: the full fp32 depth pattern
   st->depth_prefix = 0;
+  int selA = 0;
 
   int64_t N = 0;
   const double t0 = now_us();
@@ -293,18 +301,19 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (P > 0) {
     {
       StageScope sc(GAB200_STAGE_PREPROCESS, stream);
-      GAB_CUDA(cudaMemsetAsync(g.depth_range, 0xff, 2 * sizeof(uint32_t), stream));
-      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_range, stream);
+      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
+      // stage A of the key sort (per splat, by depth) + emission offsets in depth order  -- see binning.cu
       StageScope sc(GAB200_STAGE_SCAN, stream);
-      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.tiles_touched, g.offsets, P, stream));
+      GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], P, 32,
+                        &selA, stream));
+      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[selA], g.tiles_touched, g.offsets, P, stream));
     }
     GAB_STAGE_CHECK(dbg, stream);
     if (!t_slot.ok()) return GAB200_ERR_CUDA;
     GAB_CUDA(cudaMemcpyAsync(t_slot.host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    GAB_CUDA(cudaMemcpyAsync(t_slot.host + 1, g.depth_range, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
     // speculative binning allocation while the GPU is still busy with preprocess + scan
     t_sync0 = now_us();
@@ -322,15 +331,6 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
       if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
     }
     N = (int64_t)t_slot.host[0];
-    if (N > 0) {
-      const uint32_t dmin = t_slot.host[1], dmax = ~t_slot.host[2];
-      const uint32_t diff = dmin ^ dmax;
-      int db = 1;
-      while (db < 32 && (diff >> db) != 0) db++;
-      st->depth_bits = db;
-      st->depth_prefix = db >= 32 ? 0u : (dmin & ~((1u << db) - 1u));
-      st->sort_bits = db + (int)tile_bits((uint32_t)(gx * gy));
-    }
     t_sync1 = now_us();
   }
   st->num_rendered = N;
@@ -351,7 +351,8 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (N > 0) {
     {
       StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.offsets, bv.keys[0], bv.vals[0], a->exact_binning, st->depth_bits, stream);
+      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.ids[selA], g.offsets, bv.keys[0], bv.vals[0], a->exact_binning,
+                       stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {
@@ -362,7 +363,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     GAB_STAGE_CHECK(dbg, stream);
     {
       StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-      launch_tile_ranges(N, bv.keys[selector], st->depth_bits, iv.ranges, stream);
+      launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
   }
@@ -482,7 +483,10 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
   BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, a->need_backward != 0);
   ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
   const size_t N = (size_t)st->num_rendered;
-  if (keys && N) launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], st->depth_bits, st->depth_prefix, keys, stream);
+  if (keys && N) {
+    GeomView g = carve_geom(st->geom_buffer, a->P, a->need_backward != 0);
+    launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], bv.vals[st->sorted_selector], g.aux, keys, stream);
+  }
   if (values && N) GAB_CUDA(cudaMemcpyAsync(values, bv.vals[st->sorted_selector], 4 * N, cudaMemcpyDeviceToDevice, stream));
   if (ranges) GAB_CUDA(cudaMemcpyAsync(ranges, iv.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));
   return GAB200_OK;

@@ -1,37 +1,54 @@
-// binning.cu -- the two library primitives of the path (north_star: cub::DeviceRadixSort for the tile|depth keys).
-//   K2: cub::DeviceScan::InclusiveSum over tiles_touched          
-//   K4: cub::DeviceRadixSort::SortPairs on (u64 key, u32 splat id), bits [0, 32 + bits(tile id))   (K4)
-// The sort is stable, so equal (tile, depth-bits) keys keep emission order = ascending splat id: the sorted stream is
-// bit-identical to the reference's for identical keys.
+// binning.cu -- the library primitives of the path (north_star: cub::DeviceRadixSort for the tile|depth keys).
+//
+// The reference sorts N (tile << 32 | depth) 64-bit keys in one LSD radix sort.  An LSD radix sort
+// is a sequence of stable passes from the low digits to the high digits, and the low 32 bits (the depth) are the
+// same for every instance of a splat.  So the low-digit passes are done ONCE PER SPLAT, before duplication:
+//   stage A  cub::DeviceRadixSort::SortPairs (u32 depth bits, u32 splat id) over the P splats          [4 passes x 8 B x P]
+//   scan     cub::DeviceScan::InclusiveSum of tiles_touched in depth order -> emission offsets
+//   emit     instances are written in depth order with key = tile id only
+//   stage B  cub::DeviceRadixSort::SortPairs (u32 tile id, u32 splat id), bits [0, bits(tiles))        [2 passes x 8 B x N]
+// Stable passes compose: the result is exactly the reference's order (ties: ascending splat id), tested bit for bit,
+// while the N-sized traffic drops from 6 passes x 12 B to 2 passes x 8 B.
 #include <cub/cub.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include "common.cuh"
 #include "kernels.cuh"
 
 namespace gab {
 
+struct GatherTiles {
+  const uint32_t* tiles;
+  __host__ __device__ __forceinline__ uint32_t operator()(const uint32_t& id) const { return tiles[id]; }
+};
+using GatherIt = cub::TransformInputIterator<uint32_t, GatherTiles, const uint32_t*>;
+
 size_t scan_temp_bytes(int P) {
   size_t bytes = 0;
-  cub::DeviceScan::InclusiveSum(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, P);
+  GatherIt it((const uint32_t*)nullptr, GatherTiles{nullptr});
+  cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (uint32_t*)nullptr, P);
   return bytes;
 }
 
-cudaError_t run_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P, cudaStream_t stream) {
+// offsets[j] = sum_{k<=j} tiles_touched[order[k]]
+cudaError_t run_scan(void* temp, size_t temp_bytes, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* out,
+                     int P, cudaStream_t stream) {
   count_launch();
-  return cub::DeviceScan::InclusiveSum(temp, temp_bytes, in, out, P, stream);
+  GatherIt it(order, GatherTiles{tiles_touched});
+  return cub::DeviceScan::InclusiveSum(temp, temp_bytes, it, out, P, stream);
 }
 
 size_t sort_temp_bytes(int64_t N, int end_bit) {
   size_t bytes = 0;
-  cub::DoubleBuffer<uint64_t> k(nullptr, nullptr);
+  cub::DoubleBuffer<uint32_t> k(nullptr, nullptr);
   cub::DoubleBuffer<uint32_t> v(nullptr, nullptr);
   cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, N, 0, end_bit);
   return bytes;
 }
 
-cudaError_t run_sort(void* temp, size_t temp_bytes, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a,
+cudaError_t run_sort(void* temp, size_t temp_bytes, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a,
                      uint32_t* vals_b, int64_t N, int end_bit, int* selector_out, cudaStream_t stream) {
-  cub::DoubleBuffer<uint64_t> k(keys_a, keys_b);
+  cub::DoubleBuffer<uint32_t> k(keys_a, keys_b);
   cub::DoubleBuffer<uint32_t> v(vals_a, vals_b);
   cudaError_t e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, k, v, N, 0, end_bit, stream);
   // onesweep: 1 histogram + 1 scan + one pass per 8-bit digit

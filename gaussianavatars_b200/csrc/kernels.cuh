@@ -70,22 +70,23 @@ struct TileSpan {
 
 // ---- launchers (each counts its launches) ----
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, uint32_t* depth_range, cudaStream_t stream);
+                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, cudaStream_t stream);
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
-void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
-                      uint64_t* keys, uint32_t* vals, int exact_binning, int depth_bits, cudaStream_t stream);
-void launch_tile_ranges(int64_t N, const uint64_t* keys, int depth_bits, uint2* ranges, cudaStream_t stream);
-void launch_expand_keys(int64_t N, const uint64_t* keys, int depth_bits, uint32_t depth_prefix, uint64_t* out,
+void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
+                      const uint32_t* offsets, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
+void launch_tile_ranges(int64_t N, const uint32_t* keys, uint2* ranges, cudaStream_t stream);
+void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
                         cudaStream_t stream);
 void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream);
 
 // binning.cu (cub)
 size_t scan_temp_bytes(int P);
-cudaError_t run_scan(void* temp, size_t temp_bytes, const uint32_t* in, uint32_t* out, int P, cudaStream_t stream);
+cudaError_t run_scan(void* temp, size_t temp_bytes, const uint32_t* order, const uint32_t* tiles_touched, uint32_t* out,
+                     int P, cudaStream_t stream);
 size_t sort_temp_bytes(int64_t N, int end_bit);
-cudaError_t run_sort(void* temp, size_t temp_bytes, uint64_t* keys_a, uint64_t* keys_b, uint32_t* vals_a,
+cudaError_t run_sort(void* temp, size_t temp_bytes, uint32_t* keys_a, uint32_t* keys_b, uint32_t* vals_a,
                      uint32_t* vals_b, int64_t N, int end_bit, int* selector_out, cudaStream_t stream);
 
 // blend.cu

@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
                                                             SplatAux* __restrict__ aux,
                                                             uint32_t* __restrict__ tiles_touched,
                                                             uint8_t* __restrict__ clamped,
-                                                            uint32_t* __restrict__ depth_range, int exact_binning) {
+                                                            uint32_t* __restrict__ depth_keys,
+                                                            uint32_t* __restrict__ ids, int exact_binning) {
   __shared__ Camera cam;
   __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   stage_camera(a, cam);
@@ -48,12 +49,9 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, min(PRE_NT, a.P - row0), sh_width, sh_stride);
     __syncthreads();
   }
-  // lanes past the end redo splat P-1 with all writes suppressed, so that every warp reaches the warp-wide
-  // depth-range reduction below with all 32 lanes
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = idx < a.P;
-  const int i = active ? idx : a.P - 1;
-  const float* my_sh = sh_s + (active ? threadIdx.x : (a.P - 1 - blockIdx.x * PRE_NT)) * sh_stride;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.P) return;
+  const float* my_sh = sh_s + threadIdx.x * sh_stride;
   const int W = a.image_width, H = a.image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
 
@@ -206,18 +204,9 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
       }
     }
   }
-  {
-    // range of the depth bit patterns over the splats that emit instances: the sort only needs the bits that vary
-    const uint32_t db = __float_as_uint(depth_out);
-    const bool emits = active && tiles_out != 0;
-    const uint32_t lo = __reduce_min_sync(0xffffffffu, emits ? db : 0xffffffffu);
-    const uint32_t hi_inv = __reduce_min_sync(0xffffffffu, emits ? ~db : 0xffffffffu);
-    if ((threadIdx.x & 31) == 0 && lo != 0xffffffffu) {
-      atomicMin(depth_range, lo);
-      atomicMin(depth_range + 1, hi_inv);
-    }
-  }
-  if (!active) return;
+  // stage-A sort input: the fp32 depth bit pattern (splats that emit nothing go last), value = splat id
+  depth_keys[i] = tiles_out ? __float_as_uint(depth_out) : 0xffffffffu;
+  ids[i] = (uint32_t)i;
   rec[i] = out;
   SplatAux ax;
   ax.depth = depth_out; ax.radius = radius_out; ax.tiles = tiles_out; ax.pad = 0;
@@ -228,13 +217,13 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
 }
 
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, uint32_t* depth_range, cudaStream_t stream) {
+                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, cudaStream_t stream) {
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_range, a.exact_binning);
+    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning);
   else
-    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_range, a.exact_binning);
+    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning);
   count_launch();
 }
 
@@ -303,17 +292,19 @@ void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* p
 
 __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, const SplatRec* __restrict__ rec,
                                                         const SplatAux* __restrict__ aux,
+                                                        const uint32_t* __restrict__ order,
                                                         const uint32_t* __restrict__ offsets,
-                                                        uint64_t* __restrict__ keys, uint32_t* __restrict__ vals,
-                                                        int exact_binning, int depth_bits) {
+                                                        uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
+                                                        int exact_binning) {
   constexpr unsigned FULL = 0xffffffffu;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int i = warp_global * 32 + lane;
-  float px = 0.f, py = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, op = 0.f, depth = 0.f;
+  const int slot = warp_global * 32 + lane;  // position in DEPTH order; the splat it holds is order[slot]
+  float px = 0.f, py = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, op = 0.f;
   int radius = 0;
-  uint32_t ntiles = 0, off = 0;
-  if (i < P) {
+  uint32_t ntiles = 0, off = 0, i = 0;
+  if (slot < P) {
+    i = order[slot];
     const SplatAux ax = aux[i];
     ntiles = ax.tiles;
     if (ntiles) {
@@ -321,16 +312,12 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const float4 q1 = rec[i].q1;
       px = q0.x; py = q0.y; op = q1.y;
       cA = q0.z / REC_SCALE_AC; cB = q0.w / REC_SCALE_B; cC = q1.x / REC_SCALE_AC;  // undo the blend pre-scale
-      depth = ax.depth;
       radius = ax.radius;
-      off = (i == 0) ? 0u : offsets[i - 1];
+      off = (slot == 0) ? 0u : offsets[slot - 1];
     }
   }
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
   if (ntiles) tile_rect(px, py, radius, gx, gy, x0, y0, x1, y1);
-  // key = tile << depth_bits | (low depth_bits bits of the fp32 depth): the dropped high bits are identical for
-  // every emitting splat of this frame, so ascending key order == ascending (tile << 32 | depth) order
-  const uint32_t dbits = depth_bits >= 32 ? __float_as_uint(depth) : (__float_as_uint(depth) & ((1u << depth_bits) - 1u));
 
   if (exact_binning) {
     uint32_t todo = __ballot_sync(FULL, ntiles != 0);
@@ -340,11 +327,11 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const int sx0 = __shfl_sync(FULL, x0, src), sy0 = __shfl_sync(FULL, y0, src);
       const int w = __shfl_sync(FULL, x1, src) - sx0;
       const int cnt = (int)__shfl_sync(FULL, ntiles, src);
-      const uint32_t soff = __shfl_sync(FULL, off, src), sdepth = __shfl_sync(FULL, dbits, src);
-      const uint32_t sid = (uint32_t)(warp_global * 32 + src);
+      const uint32_t soff = __shfl_sync(FULL, off, src);
+      const uint32_t sid = __shfl_sync(FULL, i, src);
       for (int t = lane; t < cnt; t += 32) {
         const int y = sy0 + t / w, x = sx0 + t % w;
-        keys[soff + t] = ((uint64_t)(uint32_t)(y * gx + x) << depth_bits) | sdepth;
+        keys[soff + t] = (uint32_t)(y * gx + x);
         vals[soff + t] = sid;
       }
     }
@@ -360,8 +347,8 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       int cx0, cx1;
       span.row(ty, cx0, cx1);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << depth_bits) | dbits;
-        vals[o] = (uint32_t)i;
+        keys[o] = (uint32_t)(ty * gx + x);
+        vals[o] = i;
         o++;
       }
     }
@@ -376,8 +363,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
     const int sx0 = __shfl_sync(FULL, x0, src), sx1 = __shfl_sync(FULL, x1, src);
     const int sy0 = __shfl_sync(FULL, y0, src), sy1 = __shfl_sync(FULL, y1, src);
     uint32_t base = __shfl_sync(FULL, off, src);
-    const uint32_t sdepth = __shfl_sync(FULL, dbits, src);
-    const uint32_t sid = (uint32_t)(warp_global * 32 + src);
+    const uint32_t sid = __shfl_sync(FULL, i, src);
     TileSpan span(spx, spy, sA, sB, sC, sop, sx0, sx1);
     for (int r0 = sy0; r0 < sy1; r0 += 32) {  // 32 rows at a time: lane = row
       const int ty = r0 + lane;
@@ -392,7 +378,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       }
       uint32_t o = base + (uint32_t)(incl - len);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = ((uint64_t)(uint32_t)(ty * gx + x) << depth_bits) | sdepth;
+        keys[o] = (uint32_t)(ty * gx + x);
         vals[o] = sid;
         o++;
       }
@@ -401,27 +387,27 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   }
 }
 
-void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* offsets,
-                      uint64_t* keys, uint32_t* vals, int exact_binning, int depth_bits, cudaStream_t stream) {
+void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
+                      const uint32_t* offsets, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, offsets, keys, vals, exact_binning, depth_bits);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, keys, vals, exact_binning);
   count_launch();
 }
 
 // =====================================================================================================
 // K5: tile ranges from key transitions in the sorted stream (ranges pre-zeroed by the caller).
 // =====================================================================================================
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint64_t* __restrict__ keys,
-                                                          int depth_bits, uint2* __restrict__ ranges) {
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint32_t* __restrict__ keys,
+                                                          uint2* __restrict__ ranges) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
-  const uint32_t cur = (uint32_t)(keys[idx] >> depth_bits);
+  const uint32_t cur = keys[idx];
   if (idx == 0)
     ranges[cur].x = 0;
   else {
-    const uint32_t prev = (uint32_t)(keys[idx - 1] >> depth_bits);
+    const uint32_t prev = keys[idx - 1];
     if (cur != prev) {
       ranges[prev].y = (uint32_t)idx;
       ranges[cur].x = (uint32_t)idx;
@@ -489,27 +475,25 @@ void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t
   count_launch();
 }
 
-__global__ void expand_keys_kernel(int64_t N, const uint64_t* __restrict__ keys, int depth_bits, uint32_t prefix,
-                                   uint64_t* __restrict__ out) {
+__global__ void expand_keys_kernel(int64_t N, const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ ids,
+                                   const SplatAux* __restrict__ aux, uint64_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const uint64_t k = keys[i];
-  const uint64_t low = depth_bits >= 32 ? (k & 0xffffffffull) : (k & ((1ull << depth_bits) - 1ull));
-  out[i] = ((k >> depth_bits) << 32) | (uint64_t)prefix | low;
+  out[i] = ((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(aux[ids[i]].depth);
 }
-// the reference's key format (tile << 32 | fp32 depth bits) from the compact sort keys (parity export)
-void launch_expand_keys(int64_t N, const uint64_t* keys, int depth_bits, uint32_t depth_prefix, uint64_t* out,
+// the reference's key format (tile << 32 | fp32 depth bits) rebuilt from the two-stage sort's outputs (parity export)
+void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
                         cudaStream_t stream) {
   if (N == 0) return;
-  expand_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, keys, depth_bits, depth_prefix, out);
+  expand_keys_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(N, tile_keys, ids, aux, out);
   count_launch();
 }
 
-void launch_tile_ranges(int64_t N, const uint64_t* keys, int depth_bits, uint2* ranges, cudaStream_t stream) {
+void launch_tile_ranges(int64_t N, const uint32_t* keys, uint2* ranges, cudaStream_t stream) {
   if (N == 0) return;
   const int threads = 256;
   const int64_t blocks = (N + threads - 1) / threads;
-  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, keys, depth_bits, ranges);
+  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, keys, ranges);
   count_launch();
 }
 

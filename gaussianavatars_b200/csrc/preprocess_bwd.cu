@@ -12,7 +12,7 @@
 namespace gab {
 
 template <bool BOUND>
-__global__ void __launch_bounds__(PRE_NT, 6) preprocess_backward_kernel(gab200_backward_args b, gab200_forward_args a,
+__global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_backward_args b, gab200_forward_args a,
                                                                   const SplatRec* __restrict__ rec,
                                                                   const SplatAux* __restrict__ aux,
                                                                   const uint8_t* __restrict__ clamped,

@@ -6,7 +6,7 @@
 
 namespace gab {
 
-#define PRE_NT 128                 // threads per block of the per-splat kernels
+#define PRE_NT 64                  // threads per block of the per-splat kernels
 #define SH_SMEM_STRIDE_MAX 49      // 16 coefficients * 3 channels, padded to an odd stride
 
 // Cooperative copy of rows [row0, row0+rows) of a row-major [*, width] float matrix into shared memory with row

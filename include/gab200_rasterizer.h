@@ -118,11 +118,10 @@ typedef struct gab200_frame_state {
   void* image_buffer;
   size_t geom_bytes, binning_bytes, image_bytes;
   int32_t sorted_selector;    /* which half of the sort double-buffer holds the sorted stream */
-  int32_t sort_bits;          /* radix-sort key width used: depth_bits + bits(tile id)  (<= 32 + bits(tile id)) */
-  int32_t depth_bits;         /* the sort keys carry only the low depth_bits bits of the fp32 depth pattern: all visible
-                                 splats of the frame share the higher bits (depth_prefix), so the order is the same as
-                                 sorting the reference's full (tile << 32 | depth) key */
-  uint32_t depth_prefix;
+  int32_t sort_bits;          /* key width of the per-instance (stage B) radix sort: bits(tile id) */
+  int32_t depth_bits;         /* key width of the per-splat (stage A) radix sort: 32 (the fp32 depth pattern); the two
+                                 stable stages together are the reference's LSD sort of (tile << 32 | depth) */
+  uint32_t depth_prefix;      /* reserved (0) */
 } gab200_frame_state;
 
 /* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
