@@ -56,7 +56,20 @@ def parse():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--exact-binning", action="store_true", help="emit the reference's full instance list")
-    return ap.parse_args()
+    # other BASELINE.json configs (parity/scale cases, not the headline line): e.g. config 4 =
+    #   --gpus 8 --splats 500000 --width 2048 --height 2048 --cameras 64
+    ap.add_argument("--splats", type=int, default=None)
+    ap.add_argument("--width", type=int, default=None)
+    ap.add_argument("--height", type=int, default=None)
+    ap.add_argument("--cameras", type=int, default=None)
+    a = ap.parse_args()
+    global P_SPLATS, WIDTH, HEIGHT, N_CAMERAS, WORKLOAD
+    if a.splats or a.width or a.height or a.cameras:
+        P_SPLATS = a.splats or P_SPLATS
+        WIDTH, HEIGHT = a.width or WIDTH, a.height or HEIGHT
+        N_CAMERAS = a.cameras or N_CAMERAS
+        WORKLOAD = f"avatar-{P_SPLATS}-splats-{WIDTH}x{HEIGHT}-sh3-fused-binding-fwd+bwd ({N_CAMERAS} cameras; non-headline config)"
+    return a
 
 
 def make_cameras(n):
@@ -274,7 +287,16 @@ def main():
     h2d_bytes = gt_host[0].numel() + cam_host_blocks[0].numel() * 4
     copy_stream = torch.cuda.Stream(device=dev)
 
+    from gaussianavatars_b200 import l1_loss_u8
+
+    loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+    losses = []
+
     def step_e2e(i):
+        """Host-resident inputs -> render() -> L1 vs the uint8 ground truth -> backward -> loss scalar back on the host.
+        The scalar is copied to pinned memory asynchronously and READ one step later (every step's result is read
+        inside the timed region; the read no longer stalls the launch of the next step)."""
         cam = my_cams[i % len(my_cams)]
         zero_grads()
         with torch.cuda.stream(copy_stream):
@@ -286,11 +308,14 @@ def main():
         out = render(dcam, pc, Pipe, bg)
         torch.cuda.current_stream(dev).wait_stream(copy_stream)
         gt_u8.record_stream(torch.cuda.current_stream(dev))
-        gt = gt_u8.to(torch.float32).mul_(1.0 / 255.0)
-        loss = (out["render"] - gt).abs().mean()
+        loss = l1_loss_u8(out["render"], gt_u8)
         loss.backward()
         gdist.allreduce_splat_grads(pc)
-        return float(loss.item())  # D2H read of the step's result
+        loss_host[i % 2].copy_(loss.detach(), non_blocking=True)
+        loss_ready[i % 2].record()
+        if i > 0:
+            loss_ready[(i - 1) % 2].synchronize()
+            losses.append(float(loss_host[(i - 1) % 2]))
 
     def barrier():
         if world > 1:
@@ -345,9 +370,12 @@ def main():
     e0.record()
     for i in range(K):
         step_e2e(i)
+    loss_ready[(K - 1) % 2].synchronize()
+    losses.append(float(loss_host[(K - 1) % 2]))
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)
+    assert all(math.isfinite(v) for v in losses[-K:])
 
     def max_over_ranks(x):
         if world == 1:

@@ -5,8 +5,8 @@ gaussian_renderer.render() (reference: gaussian_renderer/__init__.py:15,37-52,86
 Nothing here falls back to CPU or eager PyTorch: the ops raise if libgaussianavatars_b200.so is missing.
 """
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, rasterize_bound,
-                         bind_activate, set_exact_binning, face_frame)
+                         bind_activate, set_exact_binning, face_frame, l1_loss_u8)
 from .renderer import render, render_bound
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_bound",
-           "bind_activate", "set_exact_binning", "face_frame", "render", "render_bound"]
+           "bind_activate", "set_exact_binning", "face_frame", "l1_loss_u8", "render", "render_bound"]

@@ -63,7 +63,7 @@ class BackwardArgs(C.Structure):
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
-                    "gab200_face_frame_backward", "gab200_host_times")
+                    "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8")
 
 _lib = None
 _lock = threading.Lock()
@@ -105,6 +105,8 @@ def lib():
         L.gab200_export_binning.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
         L.gab200_launch_count.restype = C.c_int64
+        L.gab200_l1_loss_u8.restype = C.c_int32
+        L.gab200_l1_loss_u8.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gab200_host_times.restype = None
         L.gab200_host_times.argtypes = [C.POINTER(C.c_double), C.c_int32]
         L.gab200_face_frame_forward.restype = C.c_int32

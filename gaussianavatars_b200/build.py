@@ -26,6 +26,7 @@ SOURCES = {
     "binning.cu": [],
     "blend.cu": [],
     "face_frame.cu": [],
+    "loss.cu": [],
 }
 
 

@@ -473,6 +473,15 @@ int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, con
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 
+int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n < 0 || !loss || (n > 0 && (!img || !gt || !grad))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
+  launch_l1_loss_u8(n, img, gt, grad, loss, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
 int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_state* st, uint64_t* keys,
                               uint32_t* values, uint32_t* ranges, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

@@ -260,6 +260,15 @@ void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* ord
   const int tiles = gx * gy;
   if (tiles == 0) return;
   static const int KH = env_int("GAB200_FWD_KH", 1);
+  static bool configured = false;
+  if (!configured) {
+    const int carve = env_int("GAB200_FWD_CARVEOUT", -1);
+    if (carve >= 0) {
+      cudaFuncSetAttribute(blend_forward_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(blend_forward_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+    configured = true;
+  }
   // upper bound on CTAs: every tile heavy; surplus CTAs exit at once
   const int grid = tiles;
   if (KH == 2)
@@ -459,9 +468,12 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   cp_async_wait<0>();
 }
 
+#ifndef BWD_MIN_BLOCKS
+#define BWD_MIN_BLOCKS 1
+#endif
 // CTA = 128 threads: CTAs [0, n_heavy) take one heavy tile with K = 2 (four warps); the rest take two light tiles
 // each, one per 64-thread group with K = 4.
-__global__ void __launch_bounds__(128) blend_backward_kernel(int W, int H, int gx, int tiles,
+__global__ void __launch_bounds__(128, BWD_MIN_BLOCKS) blend_backward_kernel(int W, int H, int gx, int tiles,
                                                              const uint2* __restrict__ ranges,
                                                              const uint32_t* __restrict__ order,
                                                              const uint32_t* __restrict__ order_info,
@@ -498,6 +510,12 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
+  static bool configured = false;
+  if (!configured) {  // occupancy was capped at 4 CTAs/SM by the default shared-memory carve-out (profiles/r01)
+    const int carve = env_int("GAB200_BWD_CARVEOUT", -1);
+    if (carve >= 0) cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    configured = true;
+  }
   blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
                                                    final_T, n_contrib, dL_dpix, strip_mask, g2d);
   count_launch();

@@ -109,4 +109,7 @@ void launch_face_frame_forward(int F, const float* verts, const int32_t* faces, 
 void launch_face_frame_backward(int F, const float* verts, const int32_t* faces, const float* g_fc, const float* g_fR,
                                 const float* g_fs, float* g_verts, cudaStream_t stream);
 
+// loss.cu
+void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, cudaStream_t stream);
+
 }  // namespace gab

@@ -415,3 +415,36 @@ def face_frame(verts: torch.Tensor, faces: torch.Tensor):
     """verts (V,3) [or (1,V,3)], faces (F,3) -> face_center (F,3), face_orien_mat (F,3,3), face_scaling (F,1).
     Replaces update_mesh_properties / compute_face_orientation (scene/flame_gaussian_model.py:137-147)."""
     return _FaceFrame.apply(verts, faces)
+
+
+# ================================================================================================================
+# L1 loss against a uint8 ground truth (SURVEY.md 8f rank 2): loss and dL/dimage in one kernel
+# ================================================================================================================
+class _L1LossU8(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, gt_u8):
+        device = image.device
+        if device.type != "cuda":
+            raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
+        img = _f32c(image, "image", device)
+        if gt_u8.dtype != torch.uint8 or gt_u8.numel() != img.numel():
+            raise TypeError("gt must be a uint8 tensor with the image's number of elements")
+        gt = gt_u8 if gt_u8.is_contiguous() else gt_u8.contiguous()
+        grad = torch.empty_like(img)
+        loss = torch.empty((), dtype=torch.float32, device=device)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_l1_loss_u8(img.numel(), img.data_ptr(), gt.data_ptr(), grad.data_ptr(),
+                                              loss.data_ptr(), C.c_void_p(stream)), "gab200_l1_loss_u8")
+        ctx.save_for_backward(grad)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return grad.mul_(g), None  # in place: the buffer is ours and single-use
+
+
+def l1_loss_u8(image: torch.Tensor, gt_u8: torch.Tensor) -> torch.Tensor:
+    """mean |image - gt/255| for a uint8 ground truth (same shape), differentiable w.r.t. `image`."""
+    return _L1LossU8.apply(image, gt_u8)

@@ -180,6 +180,12 @@ int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, con
                                    const float* dL_dface_center, const float* dL_dface_orien_mat,
                                    const float* dL_dface_scaling, float* dL_dverts, void* stream);
 
+/* Mean absolute error between a rendered image (n = 3*H*W floats) and a uint8 ground truth (value/255), with its
+ * gradient, in one pass: *loss = mean |img - gt/255|, grad[i] = sign(img[i] - gt[i]/255) / n.  `loss` is zeroed by the
+ * library.  Replaces `l1_loss(image, gt_image)` + its autograd and the float32 upload of the ground truth
+ * (utils/loss_utils.py:17-18, train.py:128-131); img/grad must be 16-byte aligned, gt 4-byte aligned. */
+int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, void* stream);
+
 /* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
  * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */
 int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,

@@ -432,3 +432,20 @@ def test_face_frame_kernel_matches_reference_math_and_autograd():
     assert torch.allclose(fs.cpu().double(), fr["face_scaling"].detach(), atol=1e-8, rtol=1e-5)
     ((fc * g_c.to(dev)).sum() + (fR * g_R.to(dev)).sum() + (fs * g_s.to(dev)).sum()).backward()
     h.assert_grad_close(v.grad.cpu().numpy(), v_ref.grad.numpy(), "dL/dverts of the face frame", rtol=1e-4, frac=0.0)
+
+
+def test_l1_loss_u8_kernel():
+    import gaussianavatars_b200 as g
+
+    dev = _dev()
+    gen = torch.Generator().manual_seed(0)
+    for shape in ((3, 1080, 1920), (3, 33, 17), (5,)):
+        img = torch.rand(shape, generator=gen).to(dev).requires_grad_(True)
+        gt = torch.randint(0, 256, shape, generator=gen, dtype=torch.uint8).to(dev)
+        loss = g.l1_loss_u8(img, gt)
+        (loss * 2.0).backward()
+        ref_in = img.detach().clone().requires_grad_(True)
+        ref = (ref_in - gt.float() / 255.0).abs().mean()
+        (ref * 2.0).backward()
+        assert abs(float(loss) - float(ref)) < 1e-5
+        assert torch.allclose(img.grad, ref_in.grad, atol=1e-9)
