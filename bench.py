@@ -58,6 +58,9 @@ def parse():
     ap.add_argument("--exact-binning", action="store_true", help="emit the reference's full instance list")
     # other BASELINE.json configs (parity/scale cases, not the headline line): e.g. config 4 =
     #   --gpus 8 --splats 500000 --width 2048 --height 2048 --cameras 64
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "nvls"],
+                    help="N>1 gradient reduction: one NCCL all-reduce after backward, or fused into the backward kernel "
+                         "through NVLS multicast (multimem.red); auto = nvls when the fabric supports it")
     ap.add_argument("--splats", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -254,6 +257,15 @@ def main():
     verts, faces = syn.head_mesh()
     params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
     pc = MeshBoundGaussians(params, SH_DEGREE, verts, faces, pose_fn=syn.pose_mesh, device=dev, requires_grad=True)
+    symm = None
+    if world > 1 and args.collective in ("auto", "nvls"):
+        symm = gdist.SymmetricGradBuffer(pc)
+        if symm.enabled:
+            pc.symm_grad = symm
+        else:
+            if args.collective == "nvls":
+                raise RuntimeError("NVLS multicast unavailable: " + getattr(symm, "error", "?"))
+            symm = None
     cams_host = make_cameras(N_CAMERAS)
     my_cams = [cams_host[i] for i in gdist.shard_frames(N_CAMERAS, rank, world)] or cams_host
     cams_dev = [c.to(dev) for c in my_cams]
@@ -274,8 +286,13 @@ def main():
         zero_grads()
         pc.update_mesh_properties(posed[i % len(posed)])
         out = render(cam, pc, Pipe, bg)
-        out["render"].backward(gout)
-        gdist.allreduce_splat_grads(pc)
+        if symm is not None:
+            symm.begin()
+            out["render"].backward(gout)
+            symm.end()
+        else:
+            out["render"].backward(gout)
+            gdist.allreduce_splat_grads(pc)
         return out
 
     # e2e: host-resident inputs
@@ -309,8 +326,13 @@ def main():
         torch.cuda.current_stream(dev).wait_stream(copy_stream)
         gt_u8.record_stream(torch.cuda.current_stream(dev))
         loss = l1_loss_u8(out["render"], gt_u8)
-        loss.backward()
-        gdist.allreduce_splat_grads(pc)
+        if symm is not None:
+            symm.begin()
+            loss.backward()
+            symm.end()
+        else:
+            loss.backward()
+            gdist.allreduce_splat_grads(pc)
         loss_host[i % 2].copy_(loss.detach(), non_blocking=True)
         loss_ready[i % 2].record()
         if i > 0:
@@ -416,6 +438,8 @@ def main():
         "config": {"workload": WORKLOAD, "splats": P_SPLATS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                    "faces": F, "instances_per_frame": int(n_inst), "binning": "exact" if args.exact_binning else "culled",
                    "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded dp{world}",
+                   "grad_collective": ("none" if world == 1 else ("nvls-multimem.red fused in preprocess_bwd" if symm is not None
+                                                                 else "nccl all-reduce of the flat buffer")),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
         "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},
         "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / K,

@@ -56,7 +56,7 @@ class BackwardArgs(C.Structure):
         ("dL_dopacity", C.c_void_p), ("dL_dcolors", C.c_void_p), ("dL_dshs", C.c_void_p), ("dL_dsh_dc", C.c_void_p),
         ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
         ("dL_dcov3D", C.c_void_p), ("dL_dface_center", C.c_void_p), ("dL_dface_orien_mat", C.c_void_p),
-        ("dL_dface_scaling", C.c_void_p),
+        ("dL_dface_scaling", C.c_void_p), ("grads_are_multicast", C.c_int32),
     ]
 
 

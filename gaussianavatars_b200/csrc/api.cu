@@ -415,7 +415,8 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
     if (b->dL_dface_orien_mat) GAB_CUDA(cudaMemsetAsync(b->dL_dface_orien_mat, 0, sizeof(float) * 9 * F, stream));
     if (b->dL_dface_scaling) GAB_CUDA(cudaMemsetAsync(b->dL_dface_scaling, 0, sizeof(float) * F, stream));
   }
-  if (bound && a->colors_precomp != nullptr) {
+  if (b->grads_are_multicast && !bound) return GAB200_ERR_INVALID_ARGUMENT;
+  if (bound && a->colors_precomp != nullptr && !b->grads_are_multicast) {
     if (b->dL_dsh_dc) GAB_CUDA(cudaMemsetAsync(b->dL_dsh_dc, 0, sizeof(float) * 3 * (size_t)P, stream));
     if (b->dL_dsh_rest && a->sh_coeffs > 1)
       GAB_CUDA(cudaMemsetAsync(b->dL_dsh_rest, 0, sizeof(float) * 3 * (size_t)(a->sh_coeffs - 1) * P, stream));

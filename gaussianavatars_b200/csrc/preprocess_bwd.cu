@@ -11,7 +11,7 @@
 
 namespace gab {
 
-template <bool BOUND>
+template <bool BOUND, bool MC>
 __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_backward_args b, gab200_forward_args a,
                                                                   const SplatRec* __restrict__ rec,
                                                                   const SplatAux* __restrict__ aux,
@@ -216,9 +216,9 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
     }
     // this thread is done reading its own row: overwrite it with the gradient row, then the block writes it out
     if (BOUND) {
-      if (active) {
+      if (active && (!MC || visible)) {
         float* gdc = b.dL_dsh_dc + 3 * (size_t)i;
-        gdc[0] = B[0] * gRGB[0]; gdc[1] = B[0] * gRGB[1]; gdc[2] = B[0] * gRGB[2];
+        put<MC>(gdc + 0, B[0] * gRGB[0]); put<MC>(gdc + 1, B[0] * gRGB[1]); put<MC>(gdc + 2, B[0] * gRGB[2]);
       }
       for (int k = 1; k < M; k++) {
         const float bk = (k < nb) ? B[k] : 0.f;
@@ -238,7 +238,10 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   if (stage_sh) {
     __syncthreads();
     float* dst = BOUND ? b.dL_dsh_rest : b.dL_dshs;
-    if (dst != nullptr) stage_rows_out<PRE_NT>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
+    if (dst != nullptr) stage_rows_out<PRE_NT, MC>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
+    // multicast reductions are weak operations: order them before anything this grid's completion is used to
+    // signal (the group barrier that follows the kernel on the stream)
+    if (MC) __threadfence_system();
   }
 
   // ---- Sigma -> (scale, rotation) [-> binding chain] ----
@@ -337,17 +340,18 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
 
   // ---- stores ----
   if (!active) return;
-  if (b.dL_dmeans3D != nullptr) {
-    b.dL_dmeans3D[3 * (size_t)i + 0] = g_xyz[0];
-    b.dL_dmeans3D[3 * (size_t)i + 1] = g_xyz[1];
-    b.dL_dmeans3D[3 * (size_t)i + 2] = g_xyz[2];
+  const bool emit_param = !MC || visible;  // multicast mode: splats without gradient add nothing
+  if (b.dL_dmeans3D != nullptr && emit_param) {
+    put<MC>(b.dL_dmeans3D + 3 * (size_t)i + 0, g_xyz[0]);
+    put<MC>(b.dL_dmeans3D + 3 * (size_t)i + 1, g_xyz[1]);
+    put<MC>(b.dL_dmeans3D + 3 * (size_t)i + 2, g_xyz[2]);
   }
   if (b.dL_dmeans2D != nullptr) {
     b.dL_dmeans2D[3 * (size_t)i + 0] = g2x;
     b.dL_dmeans2D[3 * (size_t)i + 1] = g2y;
     b.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
   }
-  if (b.dL_dopacity != nullptr) b.dL_dopacity[i] = g_opacity_out;
+  if (b.dL_dopacity != nullptr && emit_param) put<MC>(b.dL_dopacity + i, g_opacity_out);
   if (b.dL_dcolors != nullptr) {
     b.dL_dcolors[3 * (size_t)i + 0] = gcol[0];
     b.dL_dcolors[3 * (size_t)i + 1] = gcol[1];
@@ -357,14 +361,15 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
 #pragma unroll
     for (int k = 0; k < 6; k++) b.dL_dcov3D[6 * (size_t)i + k] = gcov[k];
   }
-  if (b.dL_dscales != nullptr) {
+  if (b.dL_dscales != nullptr && emit_param) {
 #pragma unroll
-    for (int k = 0; k < 3; k++) b.dL_dscales[3 * (size_t)i + k] = gscale[k];
+    for (int k = 0; k < 3; k++) put<MC>(b.dL_dscales + 3 * (size_t)i + k, gscale[k]);
   }
-  if (b.dL_drotations != nullptr) {
+  if (b.dL_drotations != nullptr && emit_param) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) b.dL_drotations[4 * (size_t)i + k] = grot[k];
+    for (int k = 0; k < 4; k++) put<MC>(b.dL_drotations + 4 * (size_t)i + k, grot[k]);
   }
+  if (MC) __threadfence_system();
 }
 
 void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const SplatAux* aux,
@@ -372,10 +377,14 @@ void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* r
   const gab200_forward_args& a = *b.fwd;
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
-  if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_backward_kernel<true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
-  else
-    preprocess_backward_kernel<false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+  if (a.input_mode == GAB200_INPUT_BOUND_RAW) {
+    if (b.grads_are_multicast)
+      preprocess_backward_kernel<true, true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+    else
+      preprocess_backward_kernel<true, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+  } else {
+    preprocess_backward_kernel<false, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+  }
   count_launch();
 }
 

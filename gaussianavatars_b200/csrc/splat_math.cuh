@@ -33,8 +33,23 @@ __device__ __forceinline__ void stage_rows_in(float* smem, const float* __restri
     smem[r * pstride + (q - r * width)] = src[q];
   }
 }
-// The reverse: rows staged in shared memory -> global, 128-bit stores.
-template <int NT>
+// NVLS multicast reduction: adds into the same offset of every rank's replica of a symmetric buffer (sm_90+).
+__device__ __forceinline__ void mc_red_add(float* mc_addr, float v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(mc_addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ void mc_red_add4(float* mc_addr, float4 v) {
+  asm volatile("multimem.red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+template <bool MC>
+__device__ __forceinline__ void put(float* addr, float v) {
+  if (MC) mc_red_add(addr, v);
+  else *addr = v;
+}
+
+// The reverse: rows staged in shared memory -> global, 128-bit stores (MC: 128-bit multicast reductions).
+template <int NT, bool MC = false>
 __device__ __forceinline__ void stage_rows_out(const float* smem, float* __restrict__ g, size_t row0, int rows,
                                                int width, int pstride) {
   float* dst = g + row0 * (size_t)width;
@@ -49,11 +64,16 @@ __device__ __forceinline__ void stage_rows_out(const float* smem, float* __restr
       vals[k] = smem[r * pstride + e];
       if (++e == width) { e = 0; ++r; }
     }
-    reinterpret_cast<float4*>(dst)[v] = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    const float4 o = make_float4(vals[0], vals[1], vals[2], vals[3]);
+    if (MC) {
+      if (o.x != 0.f || o.y != 0.f || o.z != 0.f || o.w != 0.f) mc_red_add4(dst + 4 * (size_t)v, o);
+    } else {
+      reinterpret_cast<float4*>(dst)[v] = o;
+    }
   }
   for (int q = nvec * 4 + threadIdx.x; q < total; q += NT) {
     const int r = q / width;
-    dst[q] = smem[r * pstride + (q - r * width)];
+    put<MC>(dst + q, smem[r * pstride + (q - r * width)]);
   }
 }
 

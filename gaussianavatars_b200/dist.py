@@ -67,3 +67,64 @@ def allreduce_densification_stats(xyz_gradient_accum, denom, max_radii2D, group=
     dist.all_reduce(xyz_gradient_accum, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(denom, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(max_radii2D, op=dist.ReduceOp.MAX, group=group)
+
+
+class SymmetricGradBuffer:
+    """The flat per-splat gradient buffer as NVLink SYMMETRIC memory with an NVLS multicast mapping.
+
+    With it attached to the model (`pc.symm_grad = SymmetricGradBuffer(pc, group)`), the fused backward does not
+    store its parameter gradients locally and all-reduce them afterwards: preprocess-backward issues
+    `multimem.red.add.f32` to the multicast address, so NVSwitch sums the ranks' contributions into EVERY rank's
+    replica while the kernel is still running (include/gab200_rasterizer.h `grads_are_multicast`).  Protocol per step:
+
+        buf.begin()      # zero the local replica, then a device-side group barrier (all replicas are zero)
+        loss.backward()  # every rank's kernel reduces into all replicas
+        buf.end()        # device-side group barrier: every replica now holds the sum
+
+    Both barriers are stream-ordered device operations (symmetric-memory signal pads); the host never blocks.
+    Falls back (attribute `.enabled` False) when the fabric has no multicast support; callers then use
+    `allreduce_splat_grads` (one NCCL all-reduce)."""
+
+    def __init__(self, pc, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self.enabled = False
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return
+        group = group if group is not None else dist.group.WORLD
+        params = list(pc.parameters())
+        self.numel = sum(p.numel() for p in params)
+        device = params[0].device
+        try:
+            try:
+                symm_mem.set_backend("CUDA")
+            except Exception:
+                pass
+            self.flat = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+            self.handle = symm_mem.rendezvous(self.flat, group)
+            self.mc_ptr = int(self.handle.multicast_ptr)
+        except Exception as e:  # pragma: no cover - fabric / build dependent
+            self.error = repr(e)
+            return
+        if self.mc_ptr == 0:
+            self.error = "no NVLS multicast support on this fabric"
+            return
+        self.enabled = True
+        self.group = group
+        self.params = params
+        # the layout of the fused backward's flat buffer: parameters in pc.parameters() order, each contiguous
+        self.views, off = [], 0
+        for p in params:
+            self.views.append(self.flat[off:off + p.numel()].view_as(p))
+            off += p.numel()
+
+    def begin(self):
+        self.flat.zero_()
+        self.handle.barrier(channel=0)
+
+    def end(self):
+        self.handle.barrier(channel=1)
+        # autograd may have CLONED the gradient views while the reduction was still in flight (it only adopts a
+        # tensor it holds the sole reference to): point .grad at the reduced buffer itself
+        for p, v in zip(self.params, self.views):
+            p.grad = v

@@ -294,7 +294,10 @@ class _RasterizeBound(torch.autograd.Function):
         # one flat buffer for all per-splat parameter gradients (dist.py all-reduces it in ONE collective):
         # [_xyz 3 | _rotation 4 | _scaling 3 | _opacity 1 | f_dc 3 | f_rest 3(M-1)]  = 59 floats/splat at SH3
         widths = (3, 4, 3, 1, 3, 3 * (M - 1))
-        flat = torch.empty((P * sum(widths),), dtype=torch.float32, device=device)
+        # frame-sharded data parallel with NVLS: the gradients are reduced INTO the symmetric buffer by the kernel
+        symm = getattr(ctx.grad_sink, "symm_grad", None) if ctx.grad_sink is not None else None
+        use_mc = symm is not None and symm.enabled and symm.numel == P * sum(widths) and colors_precomp is None
+        flat = symm.flat if use_mc else torch.empty((P * sum(widths),), dtype=torch.float32, device=device)
         views, off = [], 0
         for w in widths:
             views.append(flat[off:off + P * w])
@@ -314,10 +317,15 @@ class _RasterizeBound(torch.autograd.Function):
         b.abi_version = N.ABI_VERSION
         b.fwd, b.state = C.pointer(a), C.pointer(st)
         b.dL_dout_color = g.data_ptr()
-        b.dL_dmeans3D, b.dL_dmeans2D, b.dL_dopacity = d_xyz.data_ptr(), d_means2D.data_ptr(), d_opac.data_ptr()
+        # parameter-gradient destinations: local addresses, or the same offsets inside the NVLS multicast mapping
+        base = (symm.mc_ptr - flat.data_ptr()) if use_mc else 0
+        b.grads_are_multicast = int(use_mc)
+        b.dL_dmeans3D, b.dL_dopacity = d_xyz.data_ptr() + base, d_opac.data_ptr() + base
+        b.dL_dmeans2D = d_means2D.data_ptr()
         b.dL_dcolors = N.ptr(d_colors)
-        b.dL_dsh_dc, b.dL_dsh_rest = d_dc.data_ptr(), N.ptr(d_rest)
-        b.dL_dscales, b.dL_drotations = d_scale.data_ptr(), d_rot.data_ptr()
+        b.dL_dsh_dc = d_dc.data_ptr() + base
+        b.dL_dsh_rest = None if d_rest is None else d_rest.data_ptr() + base
+        b.dL_dscales, b.dL_drotations = d_scale.data_ptr() + base, d_rot.data_ptr() + base
         b.dL_dface_center, b.dL_dface_orien_mat, b.dL_dface_scaling = N.ptr(d_fc), N.ptr(d_fR), N.ptr(d_fs)
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
@@ -325,7 +333,6 @@ class _RasterizeBound(torch.autograd.Function):
         ctx.holder = None
         if ctx.grad_sink is not None:  # dist.py: ONE all-reduce over this buffer instead of six
             ctx.grad_sink.flat_grad = flat
-            ctx.grad_sink.flat_grad_views = (d_xyz, d_rot, d_scale, d_opac, d_dc, d_rest)
         return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None, None)
 
 

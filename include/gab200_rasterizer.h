@@ -155,6 +155,14 @@ typedef struct gab200_backward_args {
   float* dL_dface_center;
   float* dL_dface_orien_mat;
   float* dL_dface_scaling;
+  /* Fused gradient all-reduce over NVLink/NVSwitch (BOUND_RAW mode, frame-sharded data parallel).  When 1, the six
+   * parameter-gradient outputs (dL_dmeans3D, dL_drotations, dL_dscales, dL_dopacity, dL_dsh_dc, dL_dsh_rest) are
+   * NVLS MULTICAST addresses of a symmetric buffer mapped on every rank of the group, and the kernel emits
+   * multimem.red.add.f32 instead of stores: the switch sums the ranks' contributions while the backward kernel is
+   * still running -- no separate all-reduce pass.  The caller zero-fills the buffer and barriers the group before
+   * the call, and barriers again before reading the result (gaussianavatars_b200/dist.py does both).
+   * Splats that received no gradient issue nothing (the buffer already holds their zero). */
+  int32_t grads_are_multicast;
 } gab200_backward_args;
 
 int32_t gab200_backward(const gab200_backward_args* args, void* stream);
