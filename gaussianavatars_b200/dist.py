@@ -77,7 +77,7 @@ class SymmetricGradBuffer:
     `multimem.red.add.f32` to the multicast address, so NVSwitch sums the ranks' contributions into EVERY rank's
     replica while the kernel is still running (include/gab200_rasterizer.h `grads_are_multicast`).  Protocol per step:
 
-        buf.begin()      # zero the local replica, then a device-side group barrier (all replicas are zero)
+        buf.begin()      # switch to the pre-zeroed replica; zero the other one for the next step
         loss.backward()  # every rank's kernel reduces into all replicas
         buf.end()        # device-side group barrier: every replica now holds the sum
 
@@ -100,31 +100,51 @@ class SymmetricGradBuffer:
                 symm_mem.set_backend("CUDA")
             except Exception:
                 pass
-            self.flat = symm_mem.empty(self.numel, dtype=torch.float32, device=device)
-            self.handle = symm_mem.rendezvous(self.flat, group)
-            self.mc_ptr = int(self.handle.multicast_ptr)
+            # two replicas used alternately: the one for step i+1 is zeroed during step i, so that only ONE group
+            # barrier per step (end) sits on the critical path -- see begin()
+            self.flats = [symm_mem.empty(self.numel, dtype=torch.float32, device=device) for _ in range(2)]
+            self.handles = [symm_mem.rendezvous(f, group) for f in self.flats]
+            self.mc_ptrs = [int(h.multicast_ptr) for h in self.handles]
         except Exception as e:  # pragma: no cover - fabric / build dependent
             self.error = repr(e)
             return
-        if self.mc_ptr == 0:
+        if 0 in self.mc_ptrs:
             self.error = "no NVLS multicast support on this fabric"
             return
         self.enabled = True
         self.group = group
         self.params = params
         # the layout of the fused backward's flat buffer: parameters in pc.parameters() order, each contiguous
-        self.views, off = [], 0
-        for p in params:
-            self.views.append(self.flat[off:off + p.numel()].view_as(p))
-            off += p.numel()
+        self.all_views = []
+        for f in self.flats:
+            views, off = [], 0
+            for p in params:
+                views.append(f[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            self.all_views.append(views)
+        for f in self.flats:
+            f.zero_()
+        self.handles[0].barrier(channel=0)
+        self.cur = 1  # begin() flips first
+
+    @property
+    def flat(self):
+        return self.flats[self.cur]
+
+    @property
+    def mc_ptr(self):
+        return self.mc_ptrs[self.cur]
 
     def begin(self):
-        self.flat.zero_()
-        self.handle.barrier(channel=0)
+        """Call before backward.  Switches to the replica that every rank zeroed before the previous step's end()
+        barrier, and zeroes the other one (whose sums the optimizer has consumed by now) for the step after."""
+        prev = self.cur
+        self.cur ^= 1
+        self.flats[prev].zero_()
 
     def end(self):
-        self.handle.barrier(channel=1)
+        self.handles[self.cur].barrier(channel=1)
         # autograd may have CLONED the gradient views while the reduction was still in flight (it only adopts a
         # tensor it holds the sole reference to): point .grad at the reduced buffer itself
-        for p, v in zip(self.params, self.views):
+        for p, v in zip(self.params, self.all_views[self.cur]):
             p.grad = v

@@ -449,3 +449,61 @@ def test_l1_loss_u8_kernel():
         (ref * 2.0).backward()
         assert abs(float(loss) - float(ref)) < 1e-5
         assert torch.allclose(img.grad, ref_in.grad, atol=1e-9)
+
+
+@pytest.mark.parametrize("active_deg,mod", [(1, 1.0), (2, 0.8), (0, 1.0)])
+def test_active_degree_below_max_and_scale_modifier_backward(active_deg, mod):
+    """train.py raises active_sh_degree every 1000 its while 16 coefficients are stored (M=16, D<3): unused
+    coefficients must get zero gradient; scale_modifier != 1 keeps the reference's dL/dscale convention."""
+    import gaussianavatars_b200 as g
+    from oracle import rasterizer as orc
+
+    dev = _dev()
+    scene = h.random_scene(2_500, 550 // 2, 802 // 4, sh_degree=active_deg, seed=13, scale_shift=0.8, max_sh_degree=3)
+    cam = scene["cam"]
+    kw = dict(shs=scene["shs"].numpy(), sh_degree=active_deg, scales=scene["scales"].numpy(),
+              rotations=scene["rotations"].numpy(), scale_modifier=mod)
+    args = (cam.world_view_transform.numpy(), cam.full_proj_transform.numpy(), cam.camera_center.numpy())
+    st = orc.forward(scene["means3D"].numpy(), scene["opacities"].numpy(), *args, scene["W"], scene["H"], cam.tanfovx,
+                     cam.tanfovy, scene["bg"].numpy(), **kw)
+    gout = torch.randn(3, scene["H"], scene["W"], generator=torch.Generator().manual_seed(1))
+    ref = orc.backward(st, gout.numpy(), scene["means3D"].numpy(), *args, cam.tanfovx, cam.tanfovy, scene["bg"].numpy(), **kw)
+    img, radii, t, m2 = _run_cuda(scene, dev, need_grad=True, exact=False, scale_modifier=mod)
+    assert scene["shs"].shape[1] == 16
+    h.assert_image_close(img.detach().cpu().numpy(), st.out_color, "image (D < max degree)")
+    (img * gout.to(dev)).sum().backward()
+    for name in ("means3D", "scales", "rotations", "opacities", "shs"):
+        h.assert_grad_close(t[name].grad.cpu().numpy(), ref[name], f"dL/d{name}")
+    nb = (active_deg + 1) ** 2
+    assert float(t["shs"].grad[:, nb:].abs().sum()) == 0.0
+
+
+def test_fused_route_with_override_color_and_benchmark_resolution():
+    """render(..., override_color=...) on the fused route at the reference's default benchmark size 550x802
+    (fps_benchmark_demo.py:78-80; 550 is not a multiple of 16)."""
+    from gaussianavatars_b200.model import MeshBoundGaussians
+    from gaussianavatars_b200.renderer import render
+
+    dev = _dev()
+    sc = h.avatar_scene(P=9_000, W=550, H=802, seed=4, n_lat=14, n_lon=24, scale_gain=1.5)
+
+    class Pipe:
+        debug = False
+        compute_cov3D_python = False
+        convert_SHs_python = False
+
+    outs = []
+    for fused in (True, False):
+        pc = MeshBoundGaussians(sc["params"], 3, sc["verts"], sc["faces"], device=dev, requires_grad=True)
+        pc.select_mesh_by_timestep(0)
+        col = torch.rand(9_000, 3, generator=torch.Generator().manual_seed(5)).to(dev).requires_grad_(True)
+        out = render(sc["cam"], pc, Pipe, sc["bg"].to(dev), override_color=col, fused=fused)
+        out["render"].square().sum().backward()
+        outs.append((out, pc, col))
+    (o1, p1, c1), (o2, p2, c2) = outs
+    assert o1["render"].shape == (3, 802, 550)
+    h.assert_image_close(o1["render"].detach().cpu().numpy(), o2["render"].detach().cpu().numpy(), "override_color routes",
+                         frac=2e-4)
+    h.assert_grad_close(c1.grad.cpu().numpy(), c2.grad.cpu().numpy(), "dL/doverride_color", rtol=3e-3)
+    h.assert_grad_close(p1._xyz.grad.cpu().numpy(), p2._xyz.grad.cpu().numpy(), "dL/d_xyz", rtol=3e-3)
+    assert p1._features_dc.grad is None or float(p1._features_dc.grad.abs().sum()) == 0.0
