@@ -271,7 +271,9 @@ def main():
     cams_dev = [c.to(dev) for c in my_cams]
     # posed meshes (output of the FLAME LBS, upstream of the path) are inputs resident in HBM; the per-face frame
     #  is recomputed inside every step by the library's face-frame kernel
-    posed = [syn.pose_mesh(pc.verts_rest, c.timestep).contiguous() for c in my_cams]
+    # requires_grad: --bind_to_mesh training optimises the FLAME parameters (scene/flame_gaussian_model.py:186-207), so
+    # the step includes dL/d(face frame) and the face-frame backward down to the vertices
+    posed = [syn.pose_mesh(pc.verts_rest, c.timestep).contiguous().requires_grad_(True) for c in my_cams]
     bg = torch.ones(3, device=dev)
     gout = torch.randn(3, HEIGHT, WIDTH, generator=torch.Generator().manual_seed(1)).to(dev) / (3 * HEIGHT * WIDTH)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # 2x the 126 MB L2
@@ -279,6 +281,8 @@ def main():
     def zero_grads():
         for p in pc.parameters():
             p.grad = None
+        for v in posed:
+            v.grad = None
 
     def step_resident(i):
         """HBM-resident step: everything already on the device."""

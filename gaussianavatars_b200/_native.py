@@ -57,6 +57,8 @@ class BackwardArgs(C.Structure):
         ("dL_dsh_rest", C.c_void_p), ("dL_dscales", C.c_void_p), ("dL_drotations", C.c_void_p),
         ("dL_dcov3D", C.c_void_p), ("dL_dface_center", C.c_void_p), ("dL_dface_orien_mat", C.c_void_p),
         ("dL_dface_scaling", C.c_void_p), ("grads_are_multicast", C.c_int32),
+        ("face_perm", C.c_void_p), ("face_chunk_face", C.c_void_p), ("face_chunk_start", C.c_void_p),
+        ("face_chunk_end", C.c_void_p), ("num_face_chunks", C.c_int32),
     ]
 
 

@@ -44,6 +44,7 @@ struct GeomView {
   void* sortA_temp;
   size_t sortA_temp_bytes;
   float* g2d;
+  float* face_scratch;  // [P,13] per-splat face-frame gradients (CSR route of the fused backward)
   void* scan_temp;
   size_t scan_temp_bytes;
   size_t bytes;
@@ -63,6 +64,7 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   g.sortA_temp_bytes = cached_sort_temp_bytes(P > 0 ? P : 1, 32);
   g.sortA_temp = c.take<char>(g.sortA_temp_bytes);
   g.g2d = need_backward ? c.take<float>((size_t)P * GAB_G2D_STRIDE) : nullptr;
+  g.face_scratch = need_backward ? c.take<float>((size_t)P * GAB_FACE_GRAD_STRIDE) : nullptr;
   g.scan_temp_bytes = scan_temp_bytes(P);
   g.scan_temp = c.take<char>(g.scan_temp_bytes);
   g.bytes = c.bytes();
@@ -429,7 +431,10 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
   GAB_STAGE_CHECK(dbg, stream);
   {
     StageScope sc(GAB200_STAGE_PREPROCESS_BWD, stream);
-    launch_preprocess_backward(*b, g.rec, g.aux, g.clamped, g.g2d, stream);
+    const bool csr = bound && a->binding != nullptr && b->num_face_chunks > 0 && b->face_perm && b->face_chunk_face &&
+                     b->face_chunk_start && b->face_chunk_end &&
+                     (b->dL_dface_center || b->dL_dface_orien_mat || b->dL_dface_scaling);
+    launch_preprocess_backward(*b, g.rec, g.aux, g.clamped, g.g2d, csr ? g.face_scratch : nullptr, stream);
   }
   GAB_STAGE_CHECK(dbg, stream);
   return GAB200_OK;

@@ -101,7 +101,8 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
 
 // preprocess_bwd.cu
 void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const SplatAux* aux,
-                                const uint8_t* clamped, const float* g2d, cudaStream_t stream);
+                                const uint8_t* clamped, const float* g2d, float* face_scratch, cudaStream_t stream);
+#define GAB_FACE_GRAD_STRIDE 13  // per-splat face-frame gradient record: centre 3, orientation 9, scale 1
 
 // face_frame.cu
 void launch_face_frame_forward(int F, const float* verts, const int32_t* faces, float* fc, float* fR, float* fs,

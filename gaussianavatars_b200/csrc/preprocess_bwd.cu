@@ -5,6 +5,8 @@
 // accumulates dL/d{face_center, face_orien_mat, face_scaling}.
 // Behavioural quirks of the reference module are kept (Appendix B.5): 1/(det^2+1e-7) guard, guard-band masks,
 // no quaternion-normalisation Jacobian in ACTIVATED mode, dL/dscale w.r.t. s = mod*scale without the extra mod.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "splat_math.cuh"
@@ -16,8 +18,15 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
                                                                   const SplatRec* __restrict__ rec,
                                                                   const SplatAux* __restrict__ aux,
                                                                   const uint8_t* __restrict__ clamped,
-                                                                  const float* __restrict__ g2d) {
+                                                                  const float* __restrict__ g2d,
+                                                                  float* __restrict__ face_scratch, int dbg) {
   __shared__ Camera cam;
+  __shared__ float fg_s[PRE_NT * GAB_FACE_GRAD_STRIDE];  // per-splat face-frame gradients, written out coalesced
+  float* my_fg = fg_s + threadIdx.x * GAB_FACE_GRAD_STRIDE;
+  if (BOUND && face_scratch != nullptr) {
+#pragma unroll
+    for (int k = 0; k < GAB_FACE_GRAD_STRIDE; k++) my_fg[k] = 0.f;
+  }
   {
     int t = threadIdx.x;
     if (t < 16) cam.V[t] = a.viewmatrix[t];
@@ -36,7 +45,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   const float* sh_src = BOUND ? a.sh_rest : a.shs;
   const bool stage_sh = a.colors_precomp == nullptr && sh_src != nullptr && sh_width > 0;
   if (stage_sh) {
-    if (a.sh_degree > 0) stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, rows, sh_width, sh_stride);
+    if (a.sh_degree > 0 && !(dbg & 8)) stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, rows, sh_width, sh_stride);
     __syncthreads();
   }
   float* my_sh = sh_s + threadIdx.x * sh_stride;
@@ -238,7 +247,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   if (stage_sh) {
     __syncthreads();
     float* dst = BOUND ? b.dL_dsh_rest : b.dL_dshs;
-    if (dst != nullptr) stage_rows_out<PRE_NT, MC>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
+    if (dst != nullptr && !(dbg & 2)) stage_rows_out<PRE_NT, MC>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
     // multicast reductions are weak operations: order them before anything this grid's completion is used to
     // signal (the group barrier that follows the kernel on the stream)
     if (MC) __threadfence_system();
@@ -307,7 +316,19 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
       g_xyz[1] = ctx.fs * (ctx.Rf[1] * gm[0] + ctx.Rf[4] * gm[1] + ctx.Rf[7] * gm[2]);
       g_xyz[2] = ctx.fs * (ctx.Rf[2] * gm[0] + ctx.Rf[5] * gm[1] + ctx.Rf[8] * gm[2]);
       g_opacity_out = g_op * act.opacity * (1.f - act.opacity);
-      if (ctx.face >= 0) {
+      if (ctx.face >= 0 && face_scratch != nullptr) {
+        // CSR route: leave the 13 contributions in the block's tile; face_grad_reduce_kernel sums them per face
+        g_fs += gm[0] * ctx.rx.x + gm[1] * ctx.rx.y + gm[2] * ctx.rx.z;
+        my_fg[0] = gm[0]; my_fg[1] = gm[1]; my_fg[2] = gm[2];
+        const float xl[3] = {ctx.xl.x, ctx.xl.y, ctx.xl.z};
+#pragma unroll
+        for (int r = 0; r < 3; r++)
+#pragma unroll
+          for (int c = 0; c < 3; c++)
+            my_fg[3 + 3 * r + c] = dR[3 * r + 0] * ctx.Rl[3 * c + 0] + dR[3 * r + 1] * ctx.Rl[3 * c + 1] +
+                                   dR[3 * r + 2] * ctx.Rl[3 * c + 2] + ctx.fs * gm[r] * xl[c];
+        my_fg[12] = g_fs;
+      } else if (ctx.face >= 0 && !(dbg & 1)) {
         g_fs += gm[0] * ctx.rx.x + gm[1] * ctx.rx.y + gm[2] * ctx.rx.z;
         const size_t f = (size_t)ctx.face;
         if (b.dL_dface_center != nullptr) {
@@ -338,8 +359,13 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
     // unreachable: BOUND always has scale/rotation
   }
 
+  if (BOUND && face_scratch != nullptr) {
+    __syncthreads();
+    stage_rows_out<PRE_NT>(fg_s, face_scratch, (size_t)row0, rows, GAB_FACE_GRAD_STRIDE, GAB_FACE_GRAD_STRIDE);
+  }
+
   // ---- stores ----
-  if (!active) return;
+  if (!active || (dbg & 4)) return;
   const bool emit_param = !MC || visible;  // multicast mode: splats without gradient add nothing
   if (b.dL_dmeans3D != nullptr && emit_param) {
     put<MC>(b.dL_dmeans3D + 3 * (size_t)i + 0, g_xyz[0]);
@@ -372,20 +398,54 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   if (MC) __threadfence_system();
 }
 
+// One 16-lane group per chunk (<= 64 splats of one face); lane c < 13 sums component c of the chunk's splats and
+// adds it once to the face's output (several chunks only for faces with > 64 splats).
+__global__ void __launch_bounds__(256) face_grad_reduce_kernel(int num_chunks, const int32_t* __restrict__ perm,
+                                                               const int32_t* __restrict__ chunk_face,
+                                                               const int32_t* __restrict__ chunk_start,
+                                                               const int32_t* __restrict__ chunk_end,
+                                                               const float* __restrict__ fg, float* __restrict__ d_fc,
+                                                               float* __restrict__ d_fR, float* __restrict__ d_fs) {
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4, c = threadIdx.x & 15;
+  if (g >= num_chunks || c >= GAB_FACE_GRAD_STRIDE) return;
+  const int s0 = chunk_start[g], s1 = chunk_end[g];
+  float acc = 0.f;
+  int k = s0;
+  for (; k + 4 <= s1; k += 4) {  // four independent gathers in flight
+    const int i0 = perm[k], i1 = perm[k + 1], i2 = perm[k + 2], i3 = perm[k + 3];
+    const float v0 = fg[(size_t)i0 * GAB_FACE_GRAD_STRIDE + c], v1 = fg[(size_t)i1 * GAB_FACE_GRAD_STRIDE + c];
+    const float v2 = fg[(size_t)i2 * GAB_FACE_GRAD_STRIDE + c], v3 = fg[(size_t)i3 * GAB_FACE_GRAD_STRIDE + c];
+    acc += (v0 + v1) + (v2 + v3);
+  }
+  for (; k < s1; k++) acc += fg[(size_t)perm[k] * GAB_FACE_GRAD_STRIDE + c];
+  const size_t f = (size_t)chunk_face[g];
+  float* dst = c < 3 ? (d_fc ? d_fc + 3 * f + c : nullptr)
+                     : (c < 12 ? (d_fR ? d_fR + 9 * f + (c - 3) : nullptr) : (d_fs ? d_fs + f : nullptr));
+  if (dst != nullptr) atomicAdd(dst, acc);
+}
+
 void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* rec, const SplatAux* aux,
-                                const uint8_t* clamped, const float* g2d, cudaStream_t stream) {
+                                const uint8_t* clamped, const float* g2d, float* face_scratch, cudaStream_t stream) {
   const gab200_forward_args& a = *b.fwd;
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
+  static const int dbg = getenv("GAB200_DBG_BWD") ? atoi(getenv("GAB200_DBG_BWD")) : 0;  // timing experiments only
   if (a.input_mode == GAB200_INPUT_BOUND_RAW) {
     if (b.grads_are_multicast)
-      preprocess_backward_kernel<true, true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+      preprocess_backward_kernel<true, true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch, dbg);
     else
-      preprocess_backward_kernel<true, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+      preprocess_backward_kernel<true, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch, dbg);
   } else {
-    preprocess_backward_kernel<false, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d);
+    preprocess_backward_kernel<false, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, nullptr, dbg);
   }
   count_launch();
+  if (face_scratch != nullptr && b.num_face_chunks > 0) {
+    const int groups_per_block = 256 / 16;
+    face_grad_reduce_kernel<<<(b.num_face_chunks + groups_per_block - 1) / groups_per_block, 256, 0, stream>>>(
+        b.num_face_chunks, b.face_perm, b.face_chunk_face, b.face_chunk_start, b.face_chunk_end, face_scratch,
+        b.dL_dface_center, b.dL_dface_orien_mat, b.dL_dface_scaling);
+    count_launch();
+  }
 }
 
 }  // namespace gab

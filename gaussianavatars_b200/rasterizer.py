@@ -238,6 +238,34 @@ class GaussianRasterizer(nn.Module):
 # ================================================================================================================
 # Fused surface
 # ================================================================================================================
+_face_csr_cache = {}
+
+
+def _face_csr(binding: torch.Tensor, num_faces: int, chunk: int = 64):
+    """Face-sorted view of `binding` for the backward's per-face reduction (gab200_backward_args.face_*): the binding
+    only changes at densification (scene/gaussian_model.py:472-474,495-497), so this runs once per change."""
+    key = (binding.data_ptr(), binding._version, binding.shape[0], num_faces)
+    hit = _face_csr_cache.get(key)
+    if hit is not None:
+        return hit
+    b = binding.long()
+    perm = torch.argsort(b, stable=True).to(torch.int32)
+    counts = torch.bincount(b, minlength=num_faces)
+    starts = torch.cumsum(counts, 0) - counts
+    nchunks = (counts + chunk - 1) // chunk
+    face = torch.repeat_interleave(torch.arange(num_faces, device=b.device), nchunks)
+    first = torch.cumsum(nchunks, 0) - nchunks
+    within = torch.arange(face.shape[0], device=b.device) - first[face]
+    c_start = starts[face] + within * chunk
+    c_end = torch.minimum(c_start + chunk, starts[face] + counts[face])
+    out = (perm.contiguous(), face.to(torch.int32).contiguous(), c_start.to(torch.int32).contiguous(),
+           c_end.to(torch.int32).contiguous())
+    if len(_face_csr_cache) > 8:
+        _face_csr_cache.clear()
+    _face_csr_cache[key] = out
+    return out
+
+
 class _RasterizeBound(torch.autograd.Function):
     @staticmethod
     def forward(ctx, _xyz, means2D, _rotation, _scaling, _opacity, f_dc, f_rest, face_center, face_orien_mat,
@@ -281,6 +309,9 @@ class _RasterizeBound(torch.autograd.Function):
             ctx.dims = (P, M, F)
             ctx.face_shapes = None if binding is None else (face_center.shape, face_orien_mat.shape,
                                                             face_scaling.shape)
+            # face-frame gradients are only produced when something upstream of the frame trains (FLAME parameters)
+            ctx.want_face = binding is not None and any(ctx.needs_input_grad[7:10])
+            ctx.csr = _face_csr(binding, F) if ctx.want_face else None
         ctx.mark_non_differentiable(radii)
         return color, radii
 
@@ -308,7 +339,7 @@ class _RasterizeBound(torch.autograd.Function):
         d_means2D = torch.empty((P, 3), dtype=torch.float32, device=device)
         d_colors = torch.empty((P, 3), dtype=torch.float32, device=device) if colors_precomp is not None else None
         d_fc = d_fR = d_fs = None
-        if binding is not None:
+        if ctx.want_face:
             fshape = ctx.face_shapes
             d_fc = torch.empty(fshape[0], dtype=torch.float32, device=device)
             d_fR = torch.empty(fshape[1], dtype=torch.float32, device=device)
@@ -327,6 +358,11 @@ class _RasterizeBound(torch.autograd.Function):
         b.dL_dsh_rest = None if d_rest is None else d_rest.data_ptr() + base
         b.dL_dscales, b.dL_drotations = d_scale.data_ptr() + base, d_rot.data_ptr() + base
         b.dL_dface_center, b.dL_dface_orien_mat, b.dL_dface_scaling = N.ptr(d_fc), N.ptr(d_fR), N.ptr(d_fs)
+        if ctx.csr is not None:
+            perm, c_face, c_start, c_end = ctx.csr
+            b.face_perm, b.face_chunk_face = perm.data_ptr(), c_face.data_ptr()
+            b.face_chunk_start, b.face_chunk_end = c_start.data_ptr(), c_end.data_ptr()
+            b.num_face_chunks = c_face.shape[0]
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
             N.check(N.lib().gab200_backward(C.byref(b), C.c_void_p(stream)), "gab200_backward")

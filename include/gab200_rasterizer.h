@@ -163,6 +163,16 @@ typedef struct gab200_backward_args {
    * the call, and barriers again before reading the result (gaussianavatars_b200/dist.py does both).
    * Splats that received no gradient issue nothing (the buffer already holds their zero). */
   int32_t grads_are_multicast;
+  /* Optional face-sorted view of `binding` (static between densifications, so the caller builds it once):
+   * splats of one face are split into chunks of <= 64; chunk c covers face_perm[face_chunk_start[c] ..
+   * face_chunk_end[c]) and belongs to face face_chunk_face[c].  When given (num_face_chunks > 0), the face-frame
+   * gradients are reduced per chunk by a second kernel instead of 13 global atomics per splat -- a face that owns
+   * thousands of splats (hair, teeth) no longer serialises the L2 atomic unit. */
+  const int32_t* face_perm;        /* [P] splat ids sorted by face */
+  const int32_t* face_chunk_face;  /* [num_face_chunks] */
+  const int32_t* face_chunk_start; /* [num_face_chunks] */
+  const int32_t* face_chunk_end;   /* [num_face_chunks] */
+  int32_t num_face_chunks;
 } gab200_backward_args;
 
 int32_t gab200_backward(const gab200_backward_args* args, void* stream);

@@ -18,7 +18,7 @@ FAST = os.environ.get('FAST') == '1'
 for exact in ((False,) if FAST else (True, False)):
     R.set_exact_binning(exact); R.keep_last_state(True)
     pc = MeshBoundGaussians(params, 3, verts, faces, device=dev, requires_grad=True)
-    pc.select_mesh_by_timestep(0)
+    pc.update_mesh_properties(pc.verts_rest.clone().requires_grad_(True))
     for fused in ((True,) if FAST else (True, False)):
         def step(bw=True):
             out = render(cam, pc, Pipe, bg, fused=fused)
