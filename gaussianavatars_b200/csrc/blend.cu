@@ -137,56 +137,57 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
     uint32_t lb[S];
 #pragma unroll
     for (int s_ = 0; s_ < S; s_++) lb[s_] = 0;
-    int gbase = 0;
-    bool stop = false;
-    for (int j = 0; j < cnt && !stop; j++) {
-      gbase = j & ~31;
-      const float4 q0 = cur[j].q0;
-      const float4 q1 = cur[j].q1;
-      const float dx = q0.x - fx;
-      const float tA = q0.z * dx;            // conic pre-scaled by preprocess: pw = A' dx^2 + B' dx dy + C' dy^2 (log2 units)
-      const float op = q1.y;
+    // 32-splat groups: the inner loop is branch-light and unrolled; the per-group epilogue publishes the strip bits
+    // and tests saturation once per group
+    for (int gbase = 0; gbase < cnt; gbase += 32) {
+      const int gend = min(32, cnt - gbase);
+#pragma unroll 4
+      for (int jj = 0; jj < gend; jj++) {
+        const SplatRec* r = cur + gbase + jj;
+        const float4 q0 = r->q0;
+        const float4 q1 = r->q1;
+        const float dx = q0.x - fx;
+        const float tA = q0.z * dx;  // conic pre-scaled by preprocess: pw = A' dx^2 + B' dx dy + C' dy^2 (log2 units)
 #pragma unroll
-      for (int i = 0; i < K; i++) {
-        const float dy = q0.y - fy[i];
-        const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
-        const float alpha = fminf(0.99f, op * ex2_approx(pw));
-        if (!((done >> i) & 1u) && pw <= 0.f && alpha >= ALPHA_MIN) {
-          const float test_T = T[i] * (1.f - alpha);
-          if (test_T < 0.0001f) {
-            done |= 1u << i;
-          } else {
-            const float w = alpha * T[i];
-            Cr[i] = fmaf(q1.z, w, Cr[i]);
-            Cg[i] = fmaf(q1.w, w, Cg[i]);
-            Cb[i] = fmaf(cur[j].q2.x, w, Cb[i]);
-            T[i] = test_T;
-            last[i] = pos0 + (uint32_t)j + 1u;
-            lb[i >> 1] |= 1u << (j & 31);
-          }
-        }
-      }
-      if ((j & 31) == 31 || j == cnt - 1) {  // warp-uniform
-        if (want_mask) {
-          uint32_t wh = 0;
-          const int w_ = tl >> 5;
-#pragma unroll
-          for (int s_ = 0; s_ < S; s_++) {
-            if (K == 1) {
-              const uint32_t r = __reduce_or_sync(FULLMASK, lb[0]);
-              wh |= ((r >> lane) & 1u) << w_;
+        for (int i = 0; i < K; i++) {
+          const float dy = q0.y - fy[i];
+          const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
+          const float alpha = fminf(0.99f, q1.y * ex2_approx(pw));
+          if (pw <= 0.f && alpha >= ALPHA_MIN && !((done >> i) & 1u)) {
+            const float test_T = T[i] * (1.f - alpha);
+            if (test_T < 0.0001f) {
+              done |= 1u << i;
             } else {
-              const uint32_t rlo = __reduce_or_sync(FULLMASK, lane < 16 ? lb[s_] : 0u);
-              const uint32_t rhi = __reduce_or_sync(FULLMASK, lane < 16 ? 0u : lb[s_]);
-              wh |= ((rlo >> lane) & 1u) << (w_ * K + s_);
-              wh |= ((rhi >> lane) & 1u) << (w_ * K + K / 2 + s_);
+              const float w = alpha * T[i];
+              Cr[i] = fmaf(q1.z, w, Cr[i]);
+              Cg[i] = fmaf(q1.w, w, Cg[i]);
+              Cb[i] = fmaf(r->q2.x, w, Cb[i]);
+              T[i] = test_T;
+              last[i] = pos0 + (uint32_t)(gbase + jj) + 1u;
+              lb[i >> 1] |= 1u << jj;
             }
-            lb[s_] = 0;
           }
-          if (wh) atomicOr(&smask[gbase + lane], wh);
         }
-        stop = __all_sync(FULLMASK, done == ALL);  // this warp's pixels are all saturated
       }
+      if (want_mask) {
+        uint32_t wh = 0;
+        const int w_ = tl >> 5;
+#pragma unroll
+        for (int s_ = 0; s_ < S; s_++) {
+          if (K == 1) {
+            const uint32_t rr = __reduce_or_sync(FULLMASK, lb[0]);
+            wh |= ((rr >> lane) & 1u) << w_;
+          } else {
+            const uint32_t rlo = __reduce_or_sync(FULLMASK, lane < 16 ? lb[s_] : 0u);
+            const uint32_t rhi = __reduce_or_sync(FULLMASK, lane < 16 ? 0u : lb[s_]);
+            wh |= ((rlo >> lane) & 1u) << (w_ * K + s_);
+            wh |= ((rhi >> lane) & 1u) << (w_ * K + K / 2 + s_);
+          }
+          lb[s_] = 0;
+        }
+        if (wh) atomicOr(&smask[gbase + lane], wh);
+      }
+      if (__all_sync(FULLMASK, done == ALL)) break;  // this warp's pixels are all saturated
     }
     bar.sync();  // everyone is done with this buffer before chunk c+2 is gathered into it; masks complete
     if (want_mask && tl < cnt) {
@@ -402,6 +403,7 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
     const uint32_t* cur_id = odd ? bid1 : bid0;
     const uint32_t* cur_mask = odd ? bm1 : bm0;
     const int cnt = min(NT, n - c * NT);
+#pragma unroll 2
     for (int j = 0; j < cnt; j++) {
       // the forward recorded which pixel strips this splat contributed to: no strip of this warp -> nothing to do
       if ((cur_mask[j] & my_strips) == 0) continue;
