@@ -60,7 +60,9 @@ def parse():
     #   --gpus 8 --splats 500000 --width 2048 --height 2048 --cameras 64
     ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "nvls"],
                     help="N>1 gradient reduction: one NCCL all-reduce after backward, or fused into the backward kernel "
-                         "through NVLS multicast (multimem.red); auto = nvls when the fabric supports it")
+                         "through NVLS multicast (multimem.red).  auto = nccl: measured on 2/4/8 B200s the push-style "
+                         "multicast reduction ties at N=2/4 and loses at N=8 (every replica receives N x the buffer), "
+                         "see DESIGN.md section 6")
     ap.add_argument("--splats", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -258,7 +260,7 @@ def main():
     params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
     pc = MeshBoundGaussians(params, SH_DEGREE, verts, faces, pose_fn=syn.pose_mesh, device=dev, requires_grad=True)
     symm = None
-    if world > 1 and args.collective in ("auto", "nvls"):
+    if world > 1 and args.collective == "nvls":
         symm = gdist.SymmetricGradBuffer(pc)
         if symm.enabled:
             pc.symm_grad = symm

@@ -403,7 +403,6 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
     const uint32_t* cur_id = odd ? bid1 : bid0;
     const uint32_t* cur_mask = odd ? bm1 : bm0;
     const int cnt = min(NT, n - c * NT);
-#pragma unroll 2
     for (int j = 0; j < cnt; j++) {
       // the forward recorded which pixel strips this splat contributed to: no strip of this warp -> nothing to do
       if ((cur_mask[j] & my_strips) == 0) continue;
