@@ -358,28 +358,36 @@ def main():
 
     # ---- timed region: HBM-resident, L2 flushed between steps, per-step CUDA events -------------------------
     K = args.steps
-    N.stage_timing(True)
-    N.stage_times(reset=True)
-    N.host_times(reset=True)
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
-    launches0 = N.launch_count()
-    barrier()
-    with ClockSampler(local_rank) as clk:
-        wall0 = time.perf_counter()
-        for i in range(K):
-            flush_buf.fill_(i & 0xFF)  # L2 flush (outside the step's event pair)
-            starts[i].record()
-            step_resident(i)
-            ends[i].record()
+
+    def timed_pass(stage_events: bool):
+        N.stage_timing(stage_events)
+        N.stage_times(reset=True)
+        N.host_times(reset=True)
+        starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+        l0 = N.launch_count()
         barrier()
-        wall1 = time.perf_counter()
-    launches = N.launch_count() - launches0
-    stage = N.stage_times(reset=True)
-    N.stage_timing(False)
-    host_us = N.host_times(reset=True)
-    ms_steps = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    ms_total = sum(ms_steps)
+        with ClockSampler(local_rank) as clk_:
+            w0 = time.perf_counter()
+            for i in range(K):
+                flush_buf.fill_(i & 0xFF)  # L2 flush (outside the step's event pair)
+                starts[i].record()
+                step_resident(i)
+                ends[i].record()
+            barrier()
+            w1 = time.perf_counter()
+        st_ = N.stage_times(reset=True)
+        hu_ = N.host_times(reset=True)
+        N.stage_timing(False)
+        return sum(s.elapsed_time(e) for s, e in zip(starts, ends)), N.launch_count() - l0, clk_, w1 - w0, st_, hu_
+
+    # pass 1 -- the headline number: nothing but the K steps inside the event pairs
+    ms_total, launches, clk, wall_timed, _, host_us = timed_pass(False)
+    wall0, wall1 = 0.0, wall_timed
+    # pass 2 -- the same K flushed steps again with the library's per-stage CUDA events switched on (two event records
+    # per stage per step perturb the pipeline by ~10 %, so they are kept out of pass 1): per-kernel durations for the
+    # roofline line and stage_ms
+    ms_instrumented, _, _, _, stage, _ = timed_pass(True)
 
     # ---- warm-L2 variant (no flush), whole-loop events: what a training loop actually sees -------------------
     barrier()
@@ -413,6 +421,7 @@ def main():
         return float(t.item())
 
     ms_total, ms_warm, ms_e2e = max_over_ranks(ms_total), max_over_ranks(ms_warm), max_over_ranks(ms_e2e)
+    ms_instrumented = max_over_ranks(ms_instrumented)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -460,6 +469,8 @@ def main():
                                "achieved_gbs": frame_alg / ((ms_total / K) * 1e-3) / 1e9,
                                "frac": frame_alg / ((ms_total / K) * 1e-3) / 1e9 / peak}},
         "stage_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+        "stage_ms_note": "per-stage CUDA events, measured in a second pass over the same K flushed steps "
+                         f"({ms_instrumented / K:.4f} ms/step with the events on); 'scan' = per-splat depth sort + offsets scan",
         "host_us_in_forward": {k: round(v, 1) for k, v in host_us.items()},
         "wall_s_timed_region": wall1 - wall0,
     }

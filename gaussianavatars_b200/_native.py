@@ -45,7 +45,7 @@ class FrameState(C.Structure):
         ("geom_buffer", C.c_void_p), ("binning_buffer", C.c_void_p), ("image_buffer", C.c_void_p),
         ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t), ("image_bytes", C.c_size_t),
         ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32), ("depth_bits", C.c_int32),
-        ("depth_prefix", C.c_uint32),
+        ("depth_prefix", C.c_uint32), ("binning_capacity", C.c_int64),
     ]
 
 

@@ -300,6 +300,8 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   double t_sync0 = t0, t_sync1 = t0;
   void* bin = nullptr;
   size_t bin_bytes_have = 0;
+  bool ranges_cleared = false;
+  int64_t mask_cleared_for = -1;
   if (P > 0) {
     {
       StageScope sc(GAB200_STAGE_PREPROCESS, stream);
@@ -319,10 +321,19 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
     // speculative binning allocation while the GPU is still busy with preprocess + scan
     t_sync0 = now_us();
+    // ... and everything else that does not need N: the two clears are queued behind the scan right away
+    GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+    ranges_cleared = true;
     if (a->binning_hint > 0) {
-      bin_bytes_have = carve_binning(nullptr, a->binning_hint, st->sort_bits, nb).bytes;
+      const BinView hv = carve_binning(nullptr, a->binning_hint, st->sort_bits, nb);
+      bin_bytes_have = hv.bytes;
       bin = a->alloc_binning(a->alloc_user, bin_bytes_have);
       if (bin == nullptr) return GAB200_ERR_ALLOC;
+      if (nb) {  // strip masks of up to binning_hint instances (same carve as below when N <= hint)
+        const BinView hb = carve_binning(bin, a->binning_hint, st->sort_bits, nb);
+        GAB_CUDA(cudaMemsetAsync(hb.strip_mask, 0, (size_t)a->binning_hint, stream));
+        mask_cleared_for = a->binning_hint;
+      }
     }
     const double t_alloc = now_us();
     g_host_us[2] += t_alloc - t_sync0;
@@ -338,17 +349,24 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   st->num_rendered = N;
   st->num_candidates = N;
 
-  BinView bsz = carve_binning(nullptr, N, st->sort_bits, nb);
-  if (bin == nullptr || bsz.bytes > bin_bytes_have) {
+  // keep the speculative carve (sized for the hint) when it is large enough: the layout depends on the capacity
+  int64_t cap = N;
+  if (bin != nullptr && a->binning_hint >= N) {
+    cap = a->binning_hint;
+  } else {
+    BinView bsz = carve_binning(nullptr, N, st->sort_bits, nb);
     bin = a->alloc_binning(a->alloc_user, bsz.bytes);
     if (bin == nullptr) return GAB200_ERR_ALLOC;
+    mask_cleared_for = -1;
   }
   const double t_alloc2 = now_us();
-  BinView bv = carve_binning(bin, N, st->sort_bits, nb);
+  BinView bv = carve_binning(bin, cap, st->sort_bits, nb);
+  st->binning_capacity = cap;
   st->binning_buffer = bin; st->binning_bytes = bv.bytes;
 
-  GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
-  if (bv.strip_mask != nullptr && N > 0) GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)N, stream));
+  if (!ranges_cleared) GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
+  if (bv.strip_mask != nullptr && N > 0 && mask_cleared_for < N)
+    GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)N, stream));
   int selector = 0;
   if (N > 0) {
     {
@@ -408,7 +426,7 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
   if (P == 0) return GAB200_OK;
   GeomView g = carve_geom(st->geom_buffer, P, true);
   ImageView iv = carve_image(st->image_buffer, W, H, true);
-  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, true);
+  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, st->sort_bits, true);
 
   GAB_CUDA(cudaMemsetAsync(g.g2d, 0, sizeof(float) * (size_t)P * GAB_G2D_STRIDE, stream));
   if (bound && a->binding != nullptr) {
@@ -495,7 +513,7 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
     return GAB200_ERR_INVALID_ARGUMENT;
   const int W = a->image_width, H = a->image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
-  BinView bv = carve_binning(st->binning_buffer, st->num_rendered, st->sort_bits, a->need_backward != 0);
+  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, st->sort_bits, a->need_backward != 0);
   ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
   const size_t N = (size_t)st->num_rendered;
   if (keys && N) {

@@ -420,27 +420,34 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint3
 // CTA and a tile's cost is proportional to its list length, so dispatching long lists first removes the tail where
 // a few SMs grind through 2000-deep lists while the rest idle.  Single CTA, counting sort into 64 length buckets.
 #define ORDER_NB 64
-__global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2* __restrict__ ranges,
-                                                          uint32_t* __restrict__ order,
-                                                          uint32_t* __restrict__ order_info, int heavy_fwd,
-                                                          int heavy_bwd) {
-  __shared__ uint32_t hist[ORDER_NB];
-  __shared__ uint32_t cursor[ORDER_NB];
-  if (threadIdx.x < ORDER_NB) hist[threadIdx.x] = 0;
+#define ORDER_WARPS 32
+__global__ void __launch_bounds__(32 * ORDER_WARPS) tile_order_kernel(int tiles, const uint2* __restrict__ ranges,
+                                                                      uint32_t* __restrict__ order,
+                                                                      uint32_t* __restrict__ order_info, int heavy_fwd,
+                                                                      int heavy_bwd) {
+  // counting sort by list-length bucket (descending).  Every warp owns a private histogram / cursor row, so shared
+  // atomics only collide inside a warp (most tiles share a few buckets, e.g. "empty": a single row would serialise
+  // the whole CTA); the order inside a bucket is irrelevant.
+  __shared__ uint32_t hist[ORDER_WARPS][ORDER_NB + 1];
+  __shared__ uint32_t bucket_base[ORDER_NB];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int k = threadIdx.x; k < ORDER_WARPS * (ORDER_NB + 1); k += blockDim.x) (&hist[0][0])[k] = 0;
   __syncthreads();
   auto bucket = [](uint2 r) -> int {
     const uint32_t len = r.y - r.x;
     return len == 0 ? ORDER_NB - 1 : (ORDER_NB - 2) - (int)min((uint32_t)(ORDER_NB - 2), len >> 5);
   };
-  // warp-aggregated counting sort (most tiles share a few buckets -- e.g. "empty" -- so per-thread shared-memory
-  // atomics would serialise): lanes with equal buckets elect a leader that adds the group's size once
-  const int lane = threadIdx.x & 31;
-  const int rounds = (tiles + blockDim.x - 1) / blockDim.x;
-  for (int r = 0; r < rounds; r++) {
-    const int t = r * blockDim.x + threadIdx.x;
-    const int b = t < tiles ? bucket(ranges[t]) : ORDER_NB;
-    const unsigned peers = __match_any_sync(0xffffffffu, b);
-    if (t < tiles && lane == __ffs(peers) - 1) atomicAdd(&hist[b], (uint32_t)__popc(peers));
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&hist[warp][bucket(ranges[t])], 1u);
+  __syncthreads();
+  // bucket totals and per-warp starting offsets: thread b < ORDER_NB walks the warps of bucket b
+  if (threadIdx.x < ORDER_NB) {
+    uint32_t run = 0;
+    for (int w = 0; w < ORDER_WARPS; w++) {
+      const uint32_t c = hist[w][threadIdx.x];
+      hist[w][threadIdx.x] = run;  // exclusive offset of warp w inside the bucket
+      run += c;
+    }
+    bucket_base[threadIdx.x] = run;  // total
   }
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -448,22 +455,18 @@ __global__ void __launch_bounds__(1024) tile_order_kernel(int tiles, const uint2
     // a tile is "heavy" for a pass when its list has >= heavy_* splats (multiples of 32): prefix of the order
     const int qf = min(ORDER_NB - 2, max(1, heavy_fwd >> 5)), qb = min(ORDER_NB - 2, max(1, heavy_bwd >> 5));
     for (int b = 0; b < ORDER_NB; b++) {
-      cursor[b] = run;
-      run += hist[b];
+      const uint32_t c = bucket_base[b];
+      bucket_base[b] = run;
+      run += c;
       if (b == (ORDER_NB - 2) - qf) order_info[0] = run;
       if (b == (ORDER_NB - 2) - qb) order_info[1] = run;
     }
   }
   __syncthreads();
-  for (int r = 0; r < rounds; r++) {
-    const int t = r * blockDim.x + threadIdx.x;
-    const int b = t < tiles ? bucket(ranges[t]) : ORDER_NB;
-    const unsigned peers = __match_any_sync(0xffffffffu, b);
-    const int leader = __ffs(peers) - 1;
-    uint32_t base = 0;
-    if (t < tiles && lane == leader) base = atomicAdd(&cursor[b], (uint32_t)__popc(peers));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (t < tiles) order[base + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)t;
+  (void)lane;
+  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
+    const int b = bucket(ranges[t]);
+    order[bucket_base[b] + atomicAdd(&hist[warp][b], 1u)] = (uint32_t)t;
   }
 }
 

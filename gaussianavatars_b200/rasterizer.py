@@ -241,7 +241,7 @@ class GaussianRasterizer(nn.Module):
 _face_csr_cache = {}
 
 
-def _face_csr(binding: torch.Tensor, num_faces: int, chunk: int = 64):
+def _face_csr(binding: torch.Tensor, num_faces: int, chunk: int = 16):
     """Face-sorted view of `binding` for the backward's per-face reduction (gab200_backward_args.face_*): the binding
     only changes at densification (scene/gaussian_model.py:472-474,495-497), so this runs once per change."""
     key = (binding.data_ptr(), binding._version, binding.shape[0], num_faces)

@@ -122,6 +122,8 @@ typedef struct gab200_frame_state {
   int32_t depth_bits;         /* key width of the per-splat (stage A) radix sort: 32 (the fp32 depth pattern); the two
                                  stable stages together are the reference's LSD sort of (tile << 32 | depth) */
   uint32_t depth_prefix;      /* reserved (0) */
+  int64_t binning_capacity;   /* instances the binning buffer was carved for (>= num_rendered; = binning_hint when the
+                                 speculative allocation was large enough) */
 } gab200_frame_state;
 
 /* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
@@ -164,7 +166,7 @@ typedef struct gab200_backward_args {
    * Splats that received no gradient issue nothing (the buffer already holds their zero). */
   int32_t grads_are_multicast;
   /* Optional face-sorted view of `binding` (static between densifications, so the caller builds it once):
-   * splats of one face are split into chunks of <= 64; chunk c covers face_perm[face_chunk_start[c] ..
+   * splats of one face are split into chunks (e.g. <= 16 splats); chunk c covers face_perm[face_chunk_start[c] ..
    * face_chunk_end[c]) and belongs to face face_chunk_face[c].  When given (num_face_chunks > 0), the face-frame
    * gradients are reduced per chunk by a second kernel instead of 13 global atomics per splat -- a face that owns
    * thousands of splats (hair, teeth) no longer serialises the L2 atomic unit. */
