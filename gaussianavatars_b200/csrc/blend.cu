@@ -511,12 +511,6 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
-  static bool configured = false;
-  if (!configured) {  // occupancy was capped at 4 CTAs/SM by the default shared-memory carve-out (profiles/r01)
-    const int carve = env_int("GAB200_BWD_CARVEOUT", -1);
-    if (carve >= 0) cudaFuncSetAttribute(blend_backward_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    configured = true;
-  }
   blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
                                                    final_T, n_contrib, dL_dpix, strip_mask, g2d);
   count_launch();

@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
                                                                   const SplatAux* __restrict__ aux,
                                                                   const uint8_t* __restrict__ clamped,
                                                                   const float* __restrict__ g2d,
-                                                                  float* __restrict__ face_scratch, int dbg) {
+                                                                  float* __restrict__ face_scratch) {
   __shared__ Camera cam;
   __shared__ float fg_s[PRE_NT * GAB_FACE_GRAD_STRIDE];  // per-splat face-frame gradients, written out coalesced
   float* my_fg = fg_s + threadIdx.x * GAB_FACE_GRAD_STRIDE;
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   const float* sh_src = BOUND ? a.sh_rest : a.shs;
   const bool stage_sh = a.colors_precomp == nullptr && sh_src != nullptr && sh_width > 0;
   if (stage_sh) {
-    if (a.sh_degree > 0 && !(dbg & 8)) stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, rows, sh_width, sh_stride);
+    if (a.sh_degree > 0) stage_rows_in<PRE_NT>(sh_s, sh_src, (size_t)row0, rows, sh_width, sh_stride);
     __syncthreads();
   }
   float* my_sh = sh_s + threadIdx.x * sh_stride;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   if (stage_sh) {
     __syncthreads();
     float* dst = BOUND ? b.dL_dsh_rest : b.dL_dshs;
-    if (dst != nullptr && !(dbg & 2)) stage_rows_out<PRE_NT, MC>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
+    if (dst != nullptr) stage_rows_out<PRE_NT, MC>(sh_s, dst, (size_t)row0, rows, sh_width, sh_stride);
     // multicast reductions are weak operations: order them before anything this grid's completion is used to
     // signal (the group barrier that follows the kernel on the stream)
     if (MC) __threadfence_system();
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
             my_fg[3 + 3 * r + c] = dR[3 * r + 0] * ctx.Rl[3 * c + 0] + dR[3 * r + 1] * ctx.Rl[3 * c + 1] +
                                    dR[3 * r + 2] * ctx.Rl[3 * c + 2] + ctx.fs * gm[r] * xl[c];
         my_fg[12] = g_fs;
-      } else if (ctx.face >= 0 && !(dbg & 1)) {
+      } else if (ctx.face >= 0) {
         g_fs += gm[0] * ctx.rx.x + gm[1] * ctx.rx.y + gm[2] * ctx.rx.z;
         const size_t f = (size_t)ctx.face;
         if (b.dL_dface_center != nullptr) {
@@ -365,7 +365,7 @@ __global__ void __launch_bounds__(PRE_NT, 12) preprocess_backward_kernel(gab200_
   }
 
   // ---- stores ----
-  if (!active || (dbg & 4)) return;
+  if (!active) return;
   const bool emit_param = !MC || visible;  // multicast mode: splats without gradient add nothing
   if (b.dL_dmeans3D != nullptr && emit_param) {
     put<MC>(b.dL_dmeans3D + 3 * (size_t)i + 0, g_xyz[0]);
@@ -429,14 +429,13 @@ void launch_preprocess_backward(const gab200_backward_args& b, const SplatRec* r
   const gab200_forward_args& a = *b.fwd;
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
-  static const int dbg = getenv("GAB200_DBG_BWD") ? atoi(getenv("GAB200_DBG_BWD")) : 0;  // timing experiments only
   if (a.input_mode == GAB200_INPUT_BOUND_RAW) {
     if (b.grads_are_multicast)
-      preprocess_backward_kernel<true, true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch, dbg);
+      preprocess_backward_kernel<true, true><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch);
     else
-      preprocess_backward_kernel<true, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch, dbg);
+      preprocess_backward_kernel<true, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, face_scratch);
   } else {
-    preprocess_backward_kernel<false, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, nullptr, dbg);
+    preprocess_backward_kernel<false, false><<<blocks, threads, 0, stream>>>(b, a, rec, aux, clamped, g2d, nullptr);
   }
   count_launch();
   if (face_scratch != nullptr && b.num_face_chunks > 0) {
