@@ -81,7 +81,9 @@ struct BinView {
 static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_backward) {
   BinView b;
   Carver c(base);
-  const size_t n = (size_t)(N > 0 ? N : 1);
+  // + 320: the blend kernels fetch id lists with 16-B-granular bulk copies of up to 256+4 ids that may start
+  // 3 ids before a tile's run and end past the stream's last id; the slack keeps those reads inside the buffer
+  const size_t n = (size_t)(N > 0 ? N : 1) + 320;
   b.keys[0] = c.take<uint32_t>(n);
   b.keys[1] = c.take<uint32_t>(n);
   b.vals[0] = c.take<uint32_t>(n);

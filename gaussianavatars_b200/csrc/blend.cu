@@ -59,6 +59,33 @@ __device__ __forceinline__ void gather_rec(SplatRec* dst, const SplatRec* src) {
   cp_async16(&dst->q2, &src->q2);
 }
 
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier: the per-tile splat-id lists are contiguous runs of the
+// sorted stream, so they are brought into shared memory by the copy engine, NT ids per transaction, two chunks
+// ahead of the blend, without occupying LSU slots or registers.  (The 48-B records those ids point at are a gather
+// and stay on cp.async.)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tMBAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MBAR_DONE;\n\t"
+      "bra MBAR_WAIT;\n\tMBAR_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+#define ID_RING 3  // id chunks in flight: being gathered from, next, and the one the copy engine is filling
+
 // Barrier of one thread group (NT threads, hardware barrier `id`); id 0 with NT = blockDim is __syncthreads().
 template <int NT>
 struct GroupBarrier {
@@ -80,7 +107,8 @@ struct GroupBarrier {
 // =====================================================================================================
 template <int K>
 __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
-                                             SplatRec* buf1, uint32_t* smask, int W, int H, int gx,
+                                             SplatRec* buf1, uint32_t* smask, uint32_t* ids_ring, uint64_t* mbar,
+                                             int W, int H, int gx,
                                              const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
                                              const SplatRec* __restrict__ rec, const float* __restrict__ bg,
                                              float* __restrict__ out_color, float* __restrict__ final_T,
@@ -111,22 +139,51 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   }
 
   const int nchunks = (n + NT - 1) / NT;
-  // prologue: ids of chunk 0 -> gather chunk 0; ids of chunk 1 in flight
-  uint32_t id_next = (tl < n) ? ids[tl] : 0xffffffffu;
-  if (id_next != 0xffffffffu) gather_rec(&buf0[tl], rec + id_next);
+  // ---- id pipeline: chunk k of the tile's id list -> ids_ring[k % ID_RING] by one bulk copy (TMA), completion on
+  // mbar[k % ID_RING].  Bulk copies need 16-B aligned addresses and sizes: the run starts at any 4-B offset, so the
+  // copy starts `mis` ids early and carries 4 extra ids (the surplus is never read; it stays inside the binning buffer).
+  constexpr int RING_STRIDE = NT + 4;
+  constexpr uint32_t CHUNK_BYTES = RING_STRIDE * 4;
+  const int mis = (int)(range.x & 3u);
+  const uint32_t* ids_al = ids - mis;
+  if (tl == 0) {
+#pragma unroll
+    for (int k = 0; k < ID_RING; k++) mbar_init(&mbar[k], 1);
+    mbar_fence_init();
+  }
+  bar.sync();
+  auto issue_ids = [&](int k) {  // one thread: arm the barrier with the byte count, start the copy
+    uint64_t* b = &mbar[k % ID_RING];
+    mbar_arrive_expect_tx(b, CHUNK_BYTES);
+    bulk_copy_g2s(ids_ring + (k % ID_RING) * RING_STRIDE, ids_al + (size_t)k * NT, CHUNK_BYTES, b);
+  };
+  auto wait_ids = [&](int k) { mbar_wait(&mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1)); };
+  if (tl == 0) {
+    if (nchunks > 0) issue_ids(0);
+    if (nchunks > 1) issue_ids(1);
+  }
+  // prologue: gather the records of chunk 0
+  if (nchunks > 0) {
+    wait_ids(0);
+    if (tl < n) gather_rec(&buf0[tl], rec + ids_ring[mis + tl]);
+  }
   cp_async_commit();
-  id_next = (NT + tl < n) ? ids[NT + tl] : 0xffffffffu;
 
   for (int c = 0; c < nchunks; c++) {
     SplatRec* nxt = ((c + 1) & 1) ? buf1 : buf0;
-    if (c + 1 < nchunks && id_next != 0xffffffffu) gather_rec(&nxt[tl], rec + id_next);
-    cp_async_commit();
-    {
-      const int p = (c + 2) * NT + tl;
-      id_next = (p < n) ? ids[p] : 0xffffffffu;
+    if (c + 1 < nchunks) {  // records of chunk c+1 (its ids arrived while chunk c-1 was blended)
+      wait_ids(c + 1);
+      const int p = (c + 1) * NT + tl;
+      if (p < n) gather_rec(&nxt[tl], rec + ids_ring[((c + 1) % ID_RING) * RING_STRIDE + mis + tl]);
     }
+    cp_async_commit();
+    // ids of chunk c+2: its ring slot was last read (chunk c-1) before the group barrier that closed iteration c-1
+    if (tl == 0 && c + 2 < nchunks) issue_ids(c + 2);
     cp_async_wait<1>();
-    if (bar.sync_and(done == ALL)) break;  // also publishes chunk c to the group
+    if (bar.sync_and(done == ALL)) {       // also publishes chunk c to the group
+      if (c + 2 < nchunks) wait_ids(c + 2);  // never leave with a bulk copy still landing in our shared memory
+      break;
+    }
     const SplatRec* cur = (c & 1) ? buf1 : buf0;
     const int cnt = min(NT, n - c * NT);
     const uint32_t pos0 = (uint32_t)(c * NT);
@@ -230,6 +287,8 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
                                                             uint8_t* __restrict__ strip_mask) {
   __shared__ SplatRec buf[2][256];
   __shared__ uint32_t smask[256];
+  __shared__ __align__(16) uint32_t ids_ring[4][ID_RING * (64 + 4)];  // per 64-thread group; a 256-thread tile uses it flat
+  __shared__ __align__(8) uint64_t mbar[4][ID_RING];
   constexpr int GH = KH;  // heavy tiles per CTA (256/KH threads each)
   constexpr int NTH = 256 / KH;
   const int nh = (int)order_info[0];
@@ -239,13 +298,14 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
     const int g = t / NTH, slot = b * GH + g;
     if (slot >= nh) return;
     forward_tile<KH>((int)order[slot], t - g * NTH, GroupBarrier<NTH>{GH == 1 ? 0 : 1 + g}, buf[0] + g * NTH,
-                     buf[1] + g * NTH, smask + g * NTH, W, H, gx, ranges, point_list, rec, bg, out_color, final_T,
-                     n_contrib, strip_mask);
+                     buf[1] + g * NTH, smask + g * NTH, &ids_ring[0][0] + g * (ID_RING * (NTH + 4)), mbar[g], W, H, gx,
+                     ranges, point_list, rec, bg, out_color, final_T, n_contrib, strip_mask);
   } else {
     const int g = t >> 6, slot = nh + 4 * (b - heavy_ctas) + g;
     if (slot >= tiles) return;
     forward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
-                    smask + g * 64, W, H, gx, ranges, point_list, rec, bg, out_color, final_T, n_contrib, strip_mask);
+                    smask + g * 64, ids_ring[g], mbar[g], W, H, gx, ranges, point_list, rec, bg, out_color, final_T,
+                    n_contrib, strip_mask);
   }
 }
 
