@@ -377,7 +377,8 @@ __device__ __forceinline__ float warp_reduce1(float v) {
 template <int K>
 __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
                                               SplatRec* buf1, uint32_t* bid0, uint32_t* bid1, uint32_t* bm0,
-                                              uint32_t* bm1, int* s_max, int W, int H, int gx,
+                                              uint32_t* bm1, int* s_max, uint32_t* ids_ring, uint8_t* mask_ring,
+                                              uint64_t* mbar, int W, int H, int gx,
                                               const uint2* __restrict__ ranges,
                                               const uint32_t* __restrict__ point_list,
                                               const SplatRec* __restrict__ rec, const float* __restrict__ bg,
@@ -433,30 +434,64 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   const int nchunks = (n + NT - 1) / NT;
   const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;
 
-  // reverse walk: chunk c covers positions n-1-c*NT-j (j = 0..NT-1)
-  uint32_t id_next = (tl < n) ? ids[n - 1 - tl] : 0xffffffffu;
-  uint32_t mask_next = (tl < n) ? masks[n - 1 - tl] : 0u;
-  if (id_next != 0xffffffffu && mask_next != 0) gather_rec(&buf0[tl], rec + id_next);
-  bid0[tl] = id_next;
-  bm0[tl] = mask_next;
+  // reverse walk: chunk c covers positions n-1-c*NT-j (j = 0..NT-1), i.e. the ascending run [lo_c, lo_c + NT) with
+  // lo_c = max(0, n - (c+1) NT).  Ids and strip masks of a chunk arrive by two TMA bulk copies on one mbarrier
+  // (same 16-B alignment treatment as in the forward), two chunks ahead.
+  constexpr int ID_STRIDE = NT + 4;    // u32 per ring slot
+  constexpr int MK_STRIDE = NT + 16;   // bytes per ring slot
+  constexpr uint32_t TX_BYTES = ID_STRIDE * 4 + MK_STRIDE;
+  auto chunk_lo = [&](int k) { return max(0, n - (k + 1) * NT); };
+  if (tl == 0) {
+#pragma unroll
+    for (int k = 0; k < ID_RING; k++) mbar_init(&mbar[k], 1);
+    mbar_fence_init();
+  }
+  bar.sync();
+  auto issue_lists = [&](int k) {
+    const uint32_t lo = range.x + (uint32_t)chunk_lo(k);
+    uint64_t* b = &mbar[k % ID_RING];
+    mbar_arrive_expect_tx(b, TX_BYTES);
+    bulk_copy_g2s(ids_ring + (k % ID_RING) * ID_STRIDE, point_list + (lo & ~3u), ID_STRIDE * 4, b);
+    bulk_copy_g2s(mask_ring + (k % ID_RING) * MK_STRIDE, strip_mask + (lo & ~15u), MK_STRIDE, b);
+  };
+  auto wait_lists = [&](int k) { mbar_wait(&mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1)); };
+  // this thread's (id, mask) of chunk k: reverse index p = k NT + tl  <->  position n-1-p
+  auto my_entry = [&](int k, uint32_t& id, uint32_t& mask) {
+    const int p = k * NT + tl;
+    id = 0xffffffffu;
+    mask = 0u;
+    if (p < n) {
+      const int lo = chunk_lo(k);
+      const uint32_t g0 = range.x + (uint32_t)lo;
+      const int rel = (n - 1 - p) - lo;
+      id = ids_ring[(k % ID_RING) * ID_STRIDE + (int)(g0 & 3u) + rel];
+      mask = mask_ring[(k % ID_RING) * MK_STRIDE + (int)(g0 & 15u) + rel];
+    }
+  };
+  if (tl == 0) {
+    issue_lists(0);
+    if (nchunks > 1) issue_lists(1);
+  }
+  uint32_t id_cur, mask_cur;
+  wait_lists(0);
+  my_entry(0, id_cur, mask_cur);
+  if (id_cur != 0xffffffffu && mask_cur != 0) gather_rec(&buf0[tl], rec + id_cur);
+  bid0[tl] = id_cur;
+  bm0[tl] = mask_cur;
   cp_async_commit();
-  id_next = (NT + tl < n) ? ids[n - 1 - NT - tl] : 0xffffffffu;
-  mask_next = (NT + tl < n) ? masks[n - 1 - NT - tl] : 0u;
 
   for (int c = 0; c < nchunks; c++) {
     const bool odd = (c & 1) != 0;
     if (c + 1 < nchunks) {
+      wait_lists(c + 1);
+      my_entry(c + 1, id_cur, mask_cur);
       SplatRec* nb = odd ? buf0 : buf1;
-      if (id_next != 0xffffffffu && mask_next != 0) gather_rec(&nb[tl], rec + id_next);
-      (odd ? bid0 : bid1)[tl] = id_next;
-      (odd ? bm0 : bm1)[tl] = mask_next;
+      if (id_cur != 0xffffffffu && mask_cur != 0) gather_rec(&nb[tl], rec + id_cur);
+      (odd ? bid0 : bid1)[tl] = id_cur;
+      (odd ? bm0 : bm1)[tl] = mask_cur;
     }
     cp_async_commit();
-    {
-      const int p = (c + 2) * NT + tl;
-      id_next = (p < n) ? ids[n - 1 - p] : 0xffffffffu;
-      mask_next = (p < n) ? masks[n - 1 - p] : 0u;
-    }
+    if (tl == 0 && c + 2 < nchunks) issue_lists(c + 2);
     cp_async_wait<1>();
     bar.sync();
     const SplatRec* cur = odd ? buf1 : buf0;
@@ -550,17 +585,21 @@ __global__ void __launch_bounds__(128, BWD_MIN_BLOCKS) blend_backward_kernel(int
   __shared__ uint32_t bid[2][128];
   __shared__ uint32_t bm[2][128];
   __shared__ int s_max[2];
+  __shared__ __align__(16) uint32_t ids_ring[2][ID_RING * (64 + 4)];   // per 64-thread group; a 128-thread tile uses it flat
+  __shared__ __align__(16) uint8_t mask_ring[2][ID_RING * (64 + 16)];
+  __shared__ __align__(8) uint64_t mbar[2][ID_RING];
   const int nh = (int)order_info[1];
   const int b = blockIdx.x, t = threadIdx.x;
   if (b < nh) {
-    backward_tile<2>((int)order[b], t, GroupBarrier<128>{0}, buf[0], buf[1], bid[0], bid[1], bm[0], bm[1], &s_max[0], W,
-                     H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+    backward_tile<2>((int)order[b], t, GroupBarrier<128>{0}, buf[0], buf[1], bid[0], bid[1], bm[0], bm[1], &s_max[0],
+                     &ids_ring[0][0], &mask_ring[0][0], mbar[0], W, H, gx, ranges, point_list, rec, bg, final_T,
+                     n_contrib, dL_dpix, strip_mask, g2d);
   } else {
     const int g = t >> 6, slot = nh + 2 * (b - nh) + g;
     if (slot >= tiles) return;
     backward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
-                     bid[0] + g * 64, bid[1] + g * 64, bm[0] + g * 64, bm[1] + g * 64, &s_max[g], W, H, gx, ranges,
-                     point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+                     bid[0] + g * 64, bid[1] + g * 64, bm[0] + g * 64, bm[1] + g * 64, &s_max[g], ids_ring[g], mask_ring[g],
+                     mbar[g], W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
   }
 }
 
