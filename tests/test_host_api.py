@@ -124,3 +124,35 @@ def test_render_route_selection_and_camera_cache():
     blk = R._camera_block(cam, torch.device("cpu"))
     assert R._camera_block(cam, torch.device("cpu")) is blk  # uploaded once, cached on the camera object
     assert blk[0].shape == (4, 4) and blk[2].shape == (3,)
+
+
+def test_face_csr_chunks_cover_every_splat_once():
+    """The face-sorted chunk view handed to the backward's per-face reduction (gab200_backward_args.face_*)."""
+    from gaussianavatars_b200 import rasterizer as R
+
+    g = torch.Generator().manual_seed(0)
+    F = 37
+    binding = torch.randint(0, F, (1000,), generator=g).to(torch.int32)
+    binding[:300] = 5  # a hot face (several chunks)
+    perm, c_face, c_start, c_end = R._face_csr(binding, F, chunk=16)
+    assert sorted(perm.tolist()) == list(range(1000))
+    covered = torch.zeros(1000, dtype=torch.int32)
+    for f, s, e in zip(c_face.tolist(), c_start.tolist(), c_end.tolist()):
+        assert 0 < e - s <= 16
+        ids = perm[s:e].long()
+        assert (binding[ids] == f).all()
+        covered[ids] += 1
+    assert (covered == 1).all()
+    assert R._face_csr(binding, F, chunk=16)[0] is perm  # cached per binding version
+
+
+def test_symmetric_grad_buffer_is_inert_without_a_process_group():
+    from gaussianavatars_b200 import dist as gdist
+
+    class PC:
+        def parameters(self):
+            return [torch.zeros(4, 3)]
+
+    buf = gdist.SymmetricGradBuffer(PC())
+    assert buf.enabled is False
+    assert gdist.allreduce_splat_grads(PC()) == 0
