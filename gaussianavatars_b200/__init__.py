@@ -7,6 +7,8 @@ Nothing here falls back to CPU or eager PyTorch: the ops raise if libgaussianava
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, rasterize_bound,
                          bind_activate, set_exact_binning, face_frame, l1_loss_u8)
 from .renderer import render, render_bound
+from .training import photometric_loss, Adam
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_bound",
-           "bind_activate", "set_exact_binning", "face_frame", "l1_loss_u8", "render", "render_bound"]
+           "bind_activate", "set_exact_binning", "face_frame", "l1_loss_u8", "render", "render_bound",
+           "photometric_loss", "Adam"]

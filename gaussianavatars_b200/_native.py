@@ -62,10 +62,30 @@ class BackwardArgs(C.Structure):
     ]
 
 
+class PhotometricArgs(C.Structure):
+    """Mirror of gab200_photometric_args."""
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("channels", C.c_int32), ("height", C.c_int32), ("width", C.c_int32),
+        ("gt_is_u8", C.c_int32), ("lambda_dssim", C.c_float),
+        ("image", C.c_void_p), ("gt", C.c_void_p), ("grad", C.c_void_p), ("loss", C.c_void_p), ("scratch", C.c_void_p),
+    ]
+
+
+class AdamSegment(C.Structure):
+    """Mirror of gab200_adam_segment."""
+    _fields_ = [
+        ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
+        ("n", C.c_int64), ("lr", C.c_float),
+    ]
+
+
+ADAM_MAX_SEGMENTS = 8
+
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
-                    "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8")
+                    "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8",
+                    "gab200_photometric_loss", "gab200_adam_step")
 
 _lib = None
 _lock = threading.Lock()
@@ -109,6 +129,11 @@ def lib():
         L.gab200_launch_count.restype = C.c_int64
         L.gab200_l1_loss_u8.restype = C.c_int32
         L.gab200_l1_loss_u8.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gab200_photometric_loss.restype = C.c_int32
+        L.gab200_photometric_loss.argtypes = [C.POINTER(PhotometricArgs), C.c_void_p]
+        L.gab200_adam_step.restype = C.c_int32
+        L.gab200_adam_step.argtypes = [C.c_int32, C.POINTER(AdamSegment), C.c_int64, C.c_float, C.c_float, C.c_float,
+                                       C.c_void_p]
         L.gab200_host_times.restype = None
         L.gab200_host_times.argtypes = [C.POINTER(C.c_double), C.c_int32]
         L.gab200_face_frame_forward.restype = C.c_int32

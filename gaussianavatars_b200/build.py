@@ -27,6 +27,7 @@ SOURCES = {
     "blend.cu": [],
     "face_frame.cu": [],
     "loss.cu": [],
+    "optim.cu": [],
 }
 
 

@@ -508,6 +508,35 @@ int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float*
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 
+int32_t gab200_photometric_loss(const gab200_photometric_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (a == nullptr || a->abi_version != GAB200_ABI_VERSION || a->channels < 0 || a->height < 0 || a->width < 0 ||
+      a->loss == nullptr || !(a->lambda_dssim >= 0.f && a->lambda_dssim <= 1.f))
+    return GAB200_ERR_INVALID_ARGUMENT;
+  const int64_t n = (int64_t)a->channels * a->height * a->width;
+  if (n > 0 && (!a->image || !a->gt || !a->grad || !a->scratch)) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(cudaMemsetAsync(a->loss, 0, 3 * sizeof(float), stream));
+  launch_photometric_loss(a->channels, a->height, a->width, a->image, a->gt, a->gt_is_u8, a->lambda_dssim, a->grad,
+                          a->loss, a->scratch, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segs, int64_t step, float beta1, float beta2,
+                         float eps, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_segments < 0 || (num_segments > 0 && segs == nullptr) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
+      !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f))
+    return GAB200_ERR_INVALID_ARGUMENT;
+  for (int i = 0; i < num_segments; i++) {
+    const gab200_adam_segment& s = segs[i];
+    if (s.n < 0 || (s.n > 0 && (!s.param || !s.grad || !s.exp_avg || !s.exp_avg_sq))) return GAB200_ERR_INVALID_ARGUMENT;
+  }
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  launch_adam(num_segments, segs, step, beta1, beta2, eps, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
 int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_state* st, uint64_t* keys,
                               uint32_t* values, uint32_t* ranges, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;

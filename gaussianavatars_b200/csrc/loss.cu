@@ -48,4 +48,267 @@ void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* gr
   count_launch();
 }
 
+// ================================================================================================================
+// Photometric training loss  (1 - lambda) * L1 + lambda * (1 - SSIM)  with its gradient   
+// ================================================================================================================
+// The reference evaluates SSIM with five grouped 11x11 convolutions and lets autograd run five more backwards
+// (utils/loss_utils.py:36-63, train.py:131-132): ~40 eager launches and ten (3,H,W) temporaries per step.  Here it is
+// two launches.  The Gaussian window is separable, so every 32x32 tile does an 11-tap horizontal pass out of a
+// 42x42 shared-memory tile and an 11-tap vertical pass out of the result, register-blocked (each thread produces four
+// outputs from 14 loaded values).
+//
+//   ssim_stats_kernel : mu1, mu2, E[x^2], E[y^2], E[xy]  ->  the SSIM map (summed into loss[1]) and the three partial
+//                       derivatives  ds/dmu1, ds/dE[x^2], ds/dE[xy]  per pixel (12 B/px/channel of scratch);
+//                       the L1 term is summed in the same pass (loss[0]).
+//   ssim_grad_kernel  : d(sum_p s(p))/dx(q) = (G * ds/dmu1)(q) + 2 x(q) (G * ds/dE[x^2])(q) + y(q) (G * ds/dE[xy])(q)
+//                       (G symmetric, zero padding on both sides as conv2d(padding=5) does), combined with the L1
+//                       sign term into dL/dimage; the launch also writes loss[2] = the total.
+//
+// With s = A1 A2 / (B1 B2),  A1 = 2 mu1 mu2 + C1,  A2 = 2 (E[xy] - mu1 mu2) + C2,  B1 = mu1^2 + mu2^2 + C1,
+// B2 = E[x^2] - mu1^2 + E[y^2] - mu2^2 + C2:
+//   ds/dmu1    = 2 mu2 (A2 - A1) / (B1 B2) - 2 mu1 A1 A2 (B2 - B1) / (B1 B2)^2
+//   ds/dE[x^2] = -A1 A2 / (B1 B2^2)
+//   ds/dE[xy]  = 2 A1 / (B1 B2)
+
+constexpr int LT = 32;             // tile edge (outputs)
+constexpr int LHALO = 5;           // window_size // 2
+constexpr int LIN = LT + 2 * LHALO;
+constexpr int LTAPS = 2 * LHALO + 1;
+constexpr int LSEG = 4;            // outputs per thread per pass
+constexpr int LLOAD = LSEG + LTAPS - 1;
+
+struct SsimWindow { float w[LTAPS]; };
+
+__device__ __forceinline__ float gt_value(const uint8_t* p, int64_t i) { return (float)p[i] * (1.f / 255.f); }
+__device__ __forceinline__ float gt_value(const float* p, int64_t i) { return p[i]; }
+
+template <typename GT>
+__global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const float* __restrict__ img,
+                                                         const GT* __restrict__ gt, SsimWindow win, float inv_n,
+                                                         float* __restrict__ maps, int64_t map_stride,
+                                                         float* __restrict__ loss) {
+  __shared__ float sx[LIN][LIN + 1], sy[LIN][LIN + 1];
+  __shared__ float hs[5][LIN][LT + 1];
+  __shared__ float part[2][8];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+  const int64_t plane = (int64_t)blockIdx.z * H * W;
+
+  for (int i = tid; i < LIN * LIN; i += 256) {
+    const int r = i / LIN, c = i - r * LIN;
+    const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
+    float xv = 0.f, yv = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const int64_t o = plane + (int64_t)gy * W + gx;
+      xv = img[o];
+      yv = gt_value(gt, o);
+    }
+    sx[r][c] = xv;
+    sy[r][c] = yv;
+  }
+  __syncthreads();
+
+  // horizontal pass: item = (row r, 4-column segment)
+  for (int item = tid; item < LIN * (LT / LSEG); item += 256) {
+    const int seg = item / LIN, r = item - seg * LIN;
+    const int c0 = seg * LSEG;
+    float xv[LLOAD], yv[LLOAD], xx[LLOAD], yy[LLOAD], xy[LLOAD];
+#pragma unroll
+    for (int k = 0; k < LLOAD; k++) {
+      xv[k] = sx[r][c0 + k];
+      yv[k] = sy[r][c0 + k];
+      xx[k] = xv[k] * xv[k];
+      yy[k] = yv[k] * yv[k];
+      xy[k] = xv[k] * yv[k];
+    }
+#pragma unroll
+    for (int o = 0; o < LSEG; o++) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+      for (int t = 0; t < LTAPS; t++) {
+        const float w = win.w[t];
+        a0 = fmaf(w, xv[o + t], a0);
+        a1 = fmaf(w, yv[o + t], a1);
+        a2 = fmaf(w, xx[o + t], a2);
+        a3 = fmaf(w, yy[o + t], a3);
+        a4 = fmaf(w, xy[o + t], a4);
+      }
+      hs[0][r][c0 + o] = a0;
+      hs[1][r][c0 + o] = a1;
+      hs[2][r][c0 + o] = a2;
+      hs[3][r][c0 + o] = a3;
+      hs[4][r][c0 + o] = a4;
+    }
+  }
+  __syncthreads();
+
+  // vertical pass: thread = (column, group of 4 rows)
+  const int col = tid & 31, r0 = (tid >> 5) * LSEG;
+  float out[5][LSEG];
+#pragma unroll
+  for (int q = 0; q < 5; q++) {
+    float v[LLOAD];
+#pragma unroll
+    for (int k = 0; k < LLOAD; k++) v[k] = hs[q][r0 + k][col];
+#pragma unroll
+    for (int o = 0; o < LSEG; o++) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
+      out[q][o] = a;
+    }
+  }
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  float l1_sum = 0.f, ssim_sum = 0.f;
+  const int gx = x0 + col;
+#pragma unroll
+  for (int o = 0; o < LSEG; o++) {
+    const int gy = y0 + r0 + o;
+    if (gx < W && gy < H) {
+      const float mu1 = out[0][o], mu2 = out[1][o];
+      const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+      const float s1 = out[2][o] - mu1_sq, s2 = out[3][o] - mu2_sq, s12 = out[4][o] - mu12;
+      const float A1 = 2.f * mu12 + C1, A2 = 2.f * s12 + C2;
+      const float B1 = mu1_sq + mu2_sq + C1, B2 = s1 + s2 + C2;
+      const float inv_b = 1.f / (B1 * B2);
+      const float s = A1 * A2 * inv_b;
+      const float d_mu1 = 2.f * mu2 * (A2 - A1) * inv_b - 2.f * mu1 * s * (B2 - B1) * inv_b;
+      const float d_ex2 = -s / B2;
+      const float d_exy = 2.f * A1 * inv_b;
+      const int64_t o_px = plane + (int64_t)gy * W + gx;
+      maps[o_px] = d_mu1;
+      maps[map_stride + o_px] = d_ex2;
+      maps[2 * map_stride + o_px] = d_exy;
+      ssim_sum += s;
+      l1_sum += fabsf(sx[r0 + o + LHALO][col + LHALO] - sy[r0 + o + LHALO][col + LHALO]);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    l1_sum += __shfl_xor_sync(0xffffffffu, l1_sum, m);
+    ssim_sum += __shfl_xor_sync(0xffffffffu, ssim_sum, m);
+  }
+  if (col == 0) {
+    part[0][tid >> 5] = l1_sum;
+    part[1][tid >> 5] = ssim_sum;
+  }
+  __syncthreads();
+  if (tid < 2) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; w++) s += part[tid][w];
+    atomicAdd(loss + tid, s * inv_n);
+  }
+}
+
+template <typename GT>
+__global__ void __launch_bounds__(256) ssim_grad_kernel(int H, int W, const float* __restrict__ img,
+                                                        const GT* __restrict__ gt, SsimWindow win, float inv_n,
+                                                        float lambda, const float* __restrict__ maps,
+                                                        int64_t map_stride, float* __restrict__ grad,
+                                                        float* __restrict__ loss) {
+  __shared__ float sm[3][LIN][LIN + 1];
+  __shared__ float hs[3][LIN][LT + 1];
+  const int tid = threadIdx.x;
+  const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+  const int64_t plane = (int64_t)blockIdx.z * H * W;
+
+  for (int i = tid; i < LIN * LIN; i += 256) {
+    const int r = i / LIN, c = i - r * LIN;
+    const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
+    float a = 0.f, b = 0.f, d = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      const int64_t o = plane + (int64_t)gy * W + gx;
+      a = maps[o];
+      b = maps[map_stride + o];
+      d = maps[2 * map_stride + o];
+    }
+    sm[0][r][c] = a;
+    sm[1][r][c] = b;
+    sm[2][r][c] = d;
+  }
+  __syncthreads();
+  for (int item = tid; item < LIN * (LT / LSEG); item += 256) {
+    const int seg = item / LIN, r = item - seg * LIN;
+    const int c0 = seg * LSEG;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      float v[LLOAD];
+#pragma unroll
+      for (int k = 0; k < LLOAD; k++) v[k] = sm[q][r][c0 + k];
+#pragma unroll
+      for (int o = 0; o < LSEG; o++) {
+        float a = 0.f;
+#pragma unroll
+        for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
+        hs[q][r][c0 + o] = a;
+      }
+    }
+  }
+  __syncthreads();
+  const int col = tid & 31, r0 = (tid >> 5) * LSEG;
+  float out[3][LSEG];
+#pragma unroll
+  for (int q = 0; q < 3; q++) {
+    float v[LLOAD];
+#pragma unroll
+    for (int k = 0; k < LLOAD; k++) v[k] = hs[q][r0 + k][col];
+#pragma unroll
+    for (int o = 0; o < LSEG; o++) {
+      float a = 0.f;
+#pragma unroll
+      for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
+      out[q][o] = a;
+    }
+  }
+  const int gx = x0 + col;
+  const float k_l1 = (1.f - lambda) * inv_n, k_ssim = -lambda * inv_n;
+#pragma unroll
+  for (int o = 0; o < LSEG; o++) {
+    const int gy = y0 + r0 + o;
+    if (gx < W && gy < H) {
+      const int64_t o_px = plane + (int64_t)gy * W + gx;
+      const float x = img[o_px], y = gt_value(gt, o_px);
+      const float d = x - y;
+      const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+      const float dssim = out[0][o] + 2.f * x * out[1][o] + y * out[2][o];
+      grad[o_px] = k_l1 * sgn + k_ssim * dssim;
+    }
+  }
+  // the stats kernel has completed (stream order): fold the two means into the total
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0)
+    loss[2] = (1.f - lambda) * loss[0] + lambda * (1.f - loss[1]);
+}
+
+template <typename GT>
+static void launch_photometric_t(int C, int H, int W, const float* img, const GT* gt, float lambda, float* grad,
+                                 float* loss, float* scratch, cudaStream_t stream) {
+  SsimWindow win;
+  {  // gaussian(11, 1.5) of utils/loss_utils.py:23-25, in float like the reference's torch.Tensor
+    // (the float32 taps are summed in double and rounded once: that reproduces torch.Tensor.sum()'s value)
+    float g[LTAPS];
+    double sum = 0.0;
+    for (int i = 0; i < LTAPS; i++) {
+      g[i] = (float)exp(-(double)((i - LHALO) * (i - LHALO)) / (2.0 * 1.5 * 1.5));
+      sum += (double)g[i];
+    }
+    for (int i = 0; i < LTAPS; i++) win.w[i] = g[i] / (float)sum;
+  }
+  const int64_t n = (int64_t)C * H * W;
+  const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+  ssim_stats_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, scratch, n, loss);
+  count_launch();
+  ssim_grad_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, lambda, scratch, n, grad, loss);
+  count_launch();
+}
+
+void launch_photometric_loss(int C, int H, int W, const float* img, const void* gt, int gt_is_u8, float lambda,
+                             float* grad, float* loss, float* scratch, cudaStream_t stream) {
+  if ((int64_t)C * H * W == 0) return;
+  if (gt_is_u8)
+    launch_photometric_t<uint8_t>(C, H, W, img, (const uint8_t*)gt, lambda, grad, loss, scratch, stream);
+  else
+    launch_photometric_t<float>(C, H, W, img, (const float*)gt, lambda, grad, loss, scratch, stream);
+}
+
 }  // namespace gab

@@ -206,6 +206,43 @@ int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, con
  * (utils/loss_utils.py:17-18, train.py:128-131); img/grad must be 16-byte aligned, gt 4-byte aligned. */
 int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, void* stream);
 
+/* Photometric training loss of the reference with its gradient, in two launches:
+ *   total = (1 - lambda_dssim) * mean|img - gt| + lambda_dssim * (1 - mean SSIM(img, gt))
+ * Replaces `l1_loss(image, gt) * (1 - lambda)` + `(1 - ssim(image, gt)) * lambda` and their autograd
+ * (utils/loss_utils.py:17-18,36-63; train.py:131-132): 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2,
+ * C2 = 0.03^2, mean over all channels and pixels.  image / grad: float32 [channels, height, width]; gt: the same
+ * shape as uint8 (value/255; gt_is_u8 = 1) or float32 (gt_is_u8 = 0).  loss[3] receives {L1 mean, SSIM mean, total}
+ * (zeroed by the library).  scratch: 3 * channels * height * width floats owned by the caller (the three partial-
+ * derivative maps handed from the first launch to the second). */
+typedef struct gab200_photometric_args {
+  uint32_t abi_version;
+  int32_t channels, height, width;
+  int32_t gt_is_u8;
+  float lambda_dssim;
+  const float* image;
+  const void* gt;
+  float* grad;    /* [channels, height, width]  d total / d image */
+  float* loss;    /* [3] */
+  float* scratch; /* [3, channels, height, width] */
+} gab200_photometric_args;
+int32_t gab200_photometric_loss(const gab200_photometric_args* args, void* stream);
+
+/* Adam over several parameter arrays in one launch.  Replaces `gaussians.optimizer.step()` for
+ * the splat parameter groups (scene/gaussian_model.py:213-232 builds `torch.optim.Adam(l, lr=0.0, eps=1e-15)` with one
+ * group -- and one learning rate -- per array; train.py:207-209): amsgrad off, no weight decay, bias-corrected, `step`
+ * counts from 1.  `segments` is a HOST array; every pointer inside is a device pointer to n floats. */
+#define GAB_ADAM_MAX_SEGMENTS 8 /* per launch; longer lists are split */
+typedef struct gab200_adam_segment {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  int64_t n;
+  float lr;
+} gab200_adam_segment;
+int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segments, int64_t step, float beta1,
+                         float beta2, float eps, void* stream);
+
 /* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
  * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */
 int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,

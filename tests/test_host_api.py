@@ -38,7 +38,8 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     """Compile a probe against the header with gcc and compare sizeof/offsetof with the ctypes mirrors."""
     from gaussianavatars_b200 import _native as N
 
-    fields = {"gab200_forward_args": N.ForwardArgs, "gab200_frame_state": N.FrameState, "gab200_backward_args": N.BackwardArgs}
+    fields = {"gab200_forward_args": N.ForwardArgs, "gab200_frame_state": N.FrameState, "gab200_backward_args": N.BackwardArgs,
+              "gab200_photometric_args": N.PhotometricArgs, "gab200_adam_segment": N.AdamSegment}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(){"]
     for cname, ct in fields.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')
@@ -156,3 +157,29 @@ def test_symmetric_grad_buffer_is_inert_without_a_process_group():
     buf = gdist.SymmetricGradBuffer(PC())
     assert buf.enabled is False
     assert gdist.allreduce_splat_grads(PC()) == 0
+
+
+def test_adam_keeps_the_torch_optimizer_surface():
+    """Host logic only (no launch): param_groups / names / lr scheduling / state_dict as the reference uses them
+    (scene/gaussian_model.py:222-233, :89), and the configurations that are rejected."""
+    import torch
+    import gaussianavatars_b200 as g
+
+    p = torch.nn.Parameter(torch.zeros(4, 3))
+    q = torch.nn.Parameter(torch.zeros(4, 1))
+    opt = g.Adam([{"params": [p], "lr": 1.6e-4, "name": "xyz"}, {"params": [q], "lr": 5e-2, "name": "opacity"}], lr=0.0, eps=1e-15)
+    assert isinstance(opt, torch.optim.Optimizer)
+    assert [gr["name"] for gr in opt.param_groups] == ["xyz", "opacity"]
+    for gr in opt.param_groups:
+        if gr["name"] == "xyz":
+            gr["lr"] = 1e-5
+    sd = opt.state_dict()
+    assert sd["param_groups"][0]["lr"] == 1e-5 and sd["param_groups"][0]["eps"] == 1e-15
+    opt.add_param_group({"params": [torch.nn.Parameter(torch.zeros(2))], "lr": 1e-3, "name": "pose"})
+    opt.zero_grad(set_to_none=True)
+    opt.step()                       # no gradients anywhere: nothing to launch, no error even without a GPU
+    with pytest.raises(ValueError):
+        g.Adam([p], amsgrad=True)
+    p.grad = torch.ones_like(p)
+    with pytest.raises(RuntimeError, match="no CPU or eager fallback"):
+        opt.step()
