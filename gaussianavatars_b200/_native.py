@@ -75,11 +75,12 @@ class AdamSegment(C.Structure):
     """Mirror of gab200_adam_segment."""
     _fields_ = [
         ("param", C.c_void_p), ("grad", C.c_void_p), ("exp_avg", C.c_void_p), ("exp_avg_sq", C.c_void_p),
-        ("n", C.c_int64), ("lr", C.c_float),
+        ("n", C.c_int64), ("lr", C.c_double),
     ]
 
 
 ADAM_MAX_SEGMENTS = 8
+PHOTOMETRIC_SCRATCH_HEAD = 4
 
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
@@ -132,8 +133,8 @@ def lib():
         L.gab200_photometric_loss.restype = C.c_int32
         L.gab200_photometric_loss.argtypes = [C.POINTER(PhotometricArgs), C.c_void_p]
         L.gab200_adam_step.restype = C.c_int32
-        L.gab200_adam_step.argtypes = [C.c_int32, C.POINTER(AdamSegment), C.c_int64, C.c_float, C.c_float, C.c_float,
-                                       C.c_void_p]
+        L.gab200_adam_step.argtypes = [C.c_int32, C.POINTER(AdamSegment), C.c_int64, C.c_double, C.c_double,
+                                       C.c_double, C.c_void_p]
         L.gab200_host_times.restype = None
         L.gab200_host_times.argtypes = [C.POINTER(C.c_double), C.c_int32]
         L.gab200_face_frame_forward.restype = C.c_int32

@@ -516,17 +516,19 @@ int32_t gab200_photometric_loss(const gab200_photometric_args* a, void* stream_)
   const int64_t n = (int64_t)a->channels * a->height * a->width;
   if (n > 0 && (!a->image || !a->gt || !a->grad || !a->scratch)) return GAB200_ERR_INVALID_ARGUMENT;
   if (check_arch() < 0) return GAB200_ERR_ARCH;
+  if (n > 0 && ((uintptr_t)a->scratch & 15) != 0) return GAB200_ERR_INVALID_ARGUMENT;
   GAB_CUDA(cudaMemsetAsync(a->loss, 0, 3 * sizeof(float), stream));
+  if (n > 0) GAB_CUDA(cudaMemsetAsync(a->scratch, 0, GAB_PHOTOMETRIC_SCRATCH_HEAD * sizeof(float), stream));
   launch_photometric_loss(a->channels, a->height, a->width, a->image, a->gt, a->gt_is_u8, a->lambda_dssim, a->grad,
                           a->loss, a->scratch, stream);
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 
-int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segs, int64_t step, float beta1, float beta2,
-                         float eps, void* stream_) {
+int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segs, int64_t step, double beta1,
+                         double beta2, double eps, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (num_segments < 0 || (num_segments > 0 && segs == nullptr) || step < 1 || !(beta1 >= 0.f && beta1 < 1.f) ||
-      !(beta2 >= 0.f && beta2 < 1.f) || !(eps >= 0.f))
+  if (num_segments < 0 || (num_segments > 0 && segs == nullptr) || step < 1 || !(beta1 >= 0.0 && beta1 < 1.0) ||
+      !(beta2 >= 0.0 && beta2 < 1.0) || !(eps >= 0.0))
     return GAB200_ERR_INVALID_ARGUMENT;
   for (int i = 0; i < num_segments; i++) {
     const gab200_adam_segment& s = segs[i];

@@ -117,7 +117,7 @@ void launch_photometric_loss(int C, int H, int W, const float* img, const void* 
                              float* grad, float* loss, float* scratch, cudaStream_t stream);
 
 // optim.cu
-void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, float beta1, float beta2, float eps,
+void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, double beta1, double beta2, double eps,
                  cudaStream_t stream);
 
 }  // namespace gab

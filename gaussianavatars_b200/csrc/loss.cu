@@ -16,14 +16,14 @@ __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float*
   if (i4 + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(img + i4);
     const uchar4 g = *reinterpret_cast<const uchar4*>(gt + i4);
-    const float d0 = v.x - g.x * (1.f / 255.f), d1 = v.y - g.y * (1.f / 255.f);
-    const float d2 = v.z - g.z * (1.f / 255.f), d3 = v.w - g.w * (1.f / 255.f);
+    const float d0 = v.x - __fdiv_rn((float)g.x, 255.f), d1 = v.y - __fdiv_rn((float)g.y, 255.f);
+    const float d2 = v.z - __fdiv_rn((float)g.z, 255.f), d3 = v.w - __fdiv_rn((float)g.w, 255.f);
     acc = fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
     auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
     *reinterpret_cast<float4*>(grad + i4) = make_float4(sgn(d0) * inv_n, sgn(d1) * inv_n, sgn(d2) * inv_n, sgn(d3) * inv_n);
   } else {
     for (int64_t i = i4; i < n; i++) {
-      const float d = img[i] - gt[i] * (1.f / 255.f);
+      const float d = img[i] - __fdiv_rn((float)gt[i], 255.f);
       acc += fabsf(d);
       grad[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
     }
@@ -79,14 +79,17 @@ constexpr int LLOAD = LSEG + LTAPS - 1;
 
 struct SsimWindow { float w[LTAPS]; };
 
-__device__ __forceinline__ float gt_value(const uint8_t* p, int64_t i) { return (float)p[i] * (1.f / 255.f); }
+// value / 255 with a correctly rounded division: bit-identical to the reference's `torch.from_numpy(img) / 255.0`
+// (utils/general_utils.py:21-23); a multiply by 1/255 is off by one ulp for some codes and flips sign(x - y).
+__device__ __forceinline__ float u8_unit(uint8_t v) { return __fdiv_rn((float)v, 255.f); }
+__device__ __forceinline__ float gt_value(const uint8_t* p, int64_t i) { return u8_unit(p[i]); }
 __device__ __forceinline__ float gt_value(const float* p, int64_t i) { return p[i]; }
 
 template <typename GT>
 __global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const float* __restrict__ img,
                                                          const GT* __restrict__ gt, SsimWindow win, float inv_n,
                                                          float* __restrict__ maps, int64_t map_stride,
-                                                         float* __restrict__ loss) {
+                                                         double* __restrict__ sums) {
   __shared__ float sx[LIN][LIN + 1], sy[LIN][LIN + 1];
   __shared__ float hs[5][LIN][LT + 1];
   __shared__ float part[2][8];
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const flo
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; w++) s += part[tid][w];
-    atomicAdd(loss + tid, s * inv_n);
+    atomicAdd(sums + tid, (double)s);  // ~10^3 block sums of up to 1024 terms each: float atomics would cost 1e-6
   }
 }
 
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(int H, int W, const floa
                                                         const GT* __restrict__ gt, SsimWindow win, float inv_n,
                                                         float lambda, const float* __restrict__ maps,
                                                         int64_t map_stride, float* __restrict__ grad,
-                                                        float* __restrict__ loss) {
+                                                        const double* __restrict__ sums, float* __restrict__ loss) {
   __shared__ float sm[3][LIN][LIN + 1];
   __shared__ float hs[3][LIN][LT + 1];
   const int tid = threadIdx.x;
@@ -276,8 +279,12 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(int H, int W, const floa
     }
   }
   // the stats kernel has completed (stream order): fold the two means into the total
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0)
-    loss[2] = (1.f - lambda) * loss[0] + lambda * (1.f - loss[1]);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
+    const double l1 = sums[0] * (double)inv_n, ssim = sums[1] * (double)inv_n;
+    loss[0] = (float)l1;
+    loss[1] = (float)ssim;
+    loss[2] = (float)((1.0 - (double)lambda) * l1 + (double)lambda * (1.0 - ssim));
+  }
 }
 
 template <typename GT>
@@ -296,9 +303,11 @@ static void launch_photometric_t(int C, int H, int W, const float* img, const GT
   }
   const int64_t n = (int64_t)C * H * W;
   const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
-  ssim_stats_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, scratch, n, loss);
+  double* sums = reinterpret_cast<double*>(scratch);  // [2], zeroed by the caller (api.cu); the maps follow
+  float* maps = scratch + GAB_PHOTOMETRIC_SCRATCH_HEAD;
+  ssim_stats_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, maps, n, sums);
   count_launch();
-  ssim_grad_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, lambda, scratch, n, grad, loss);
+  ssim_grad_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, lambda, maps, n, grad, sums, loss);
   count_launch();
 }
 

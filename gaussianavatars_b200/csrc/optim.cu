@@ -9,7 +9,8 @@
 //   m <- m + (g - m) (1 - beta1)                 (Tensor.lerp_)
 //   v <- beta2 v + (1 - beta2) g g               (mul_ / addcmul_)
 //   p <- p - (lr / (1 - beta1^t)) * m / (sqrt(v) / sqrt(1 - beta2^t) + eps)
-// The scalars are formed on the host in double, as torch does, and rounded to float once.
+// The scalars (1 - beta, lr / (1 - beta1^t), ...) are formed on the host in double from double hyper-parameters, as
+// torch forms them from Python floats, and rounded to float once: 1.0f - 0.999f would already be off by 1.3e-5.
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -78,10 +79,10 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b, float w1, float 
   }
 }
 
-void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, float beta1, float beta2, float eps,
+void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, double beta1, double beta2, double eps,
                  cudaStream_t stream) {
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
   for (int base = 0; base < num_segments; base += GAB_ADAM_MAX_SEGMENTS) {
     AdamBatch b;
@@ -95,7 +96,7 @@ void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step
       b.m[cnt] = s.exp_avg;
       b.v[cnt] = s.exp_avg_sq;
       b.n[cnt] = s.n;
-      b.step_size[cnt] = (float)((double)s.lr / bc1);
+      b.step_size[cnt] = (float)(s.lr / bc1);
       const uintptr_t bits = (uintptr_t)s.param | (uintptr_t)s.exp_avg | (uintptr_t)s.exp_avg_sq;
       b.vec4[cnt] = (bits & 15) == 0 ? (((uintptr_t)s.grad & 15) == 0 ? 3 : 1) : 0;
       longest = s.n > longest ? s.n : longest;
@@ -110,8 +111,8 @@ void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step
     int64_t blocks = (longest / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
-    adam_kernel<<<dim3((unsigned)blocks, (unsigned)cnt), 256, 0, stream>>>(b, 1.0f - beta1, beta2, 1.0f - beta2,
-                                                                           inv_bc2_sqrt, eps);
+    adam_kernel<<<dim3((unsigned)blocks, (unsigned)cnt), 256, 0, stream>>>(
+        b, (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2), inv_bc2_sqrt, (float)eps);
     count_launch();
   }
 }

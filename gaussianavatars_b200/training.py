@@ -38,7 +38,7 @@ class _PhotometricLoss(torch.autograd.Function):
         g = gt if gt.is_contiguous() else gt.contiguous()
         Cc, H, W = img.shape
         grad = torch.empty_like(img)
-        scratch = torch.empty((3,) + tuple(img.shape), dtype=torch.float32, device=device)
+        scratch = torch.empty(N.PHOTOMETRIC_SCRATCH_HEAD + 3 * img.numel(), dtype=torch.float32, device=device)
         loss = torch.empty(3, dtype=torch.float32, device=device)
         a = N.PhotometricArgs()
         a.abi_version = N.ABI_VERSION

@@ -212,8 +212,9 @@ int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float*
  * (utils/loss_utils.py:17-18,36-63; train.py:131-132): 11x11 Gaussian window, sigma 1.5, zero padding, C1 = 0.01^2,
  * C2 = 0.03^2, mean over all channels and pixels.  image / grad: float32 [channels, height, width]; gt: the same
  * shape as uint8 (value/255; gt_is_u8 = 1) or float32 (gt_is_u8 = 0).  loss[3] receives {L1 mean, SSIM mean, total}
- * (zeroed by the library).  scratch: 3 * channels * height * width floats owned by the caller (the three partial-
- * derivative maps handed from the first launch to the second). */
+ * scratch: GAB_PHOTOMETRIC_SCRATCH_HEAD + 3 * channels * height * width floats owned by the caller, 16-byte aligned
+ * (two double accumulators, then the three partial-derivative maps handed from the first launch to the second). */
+#define GAB_PHOTOMETRIC_SCRATCH_HEAD 4
 typedef struct gab200_photometric_args {
   uint32_t abi_version;
   int32_t channels, height, width;
@@ -223,7 +224,7 @@ typedef struct gab200_photometric_args {
   const void* gt;
   float* grad;    /* [channels, height, width]  d total / d image */
   float* loss;    /* [3] */
-  float* scratch; /* [3, channels, height, width] */
+  float* scratch; /* [GAB_PHOTOMETRIC_SCRATCH_HEAD + 3 * channels * height * width] */
 } gab200_photometric_args;
 int32_t gab200_photometric_loss(const gab200_photometric_args* args, void* stream);
 
@@ -238,10 +239,10 @@ typedef struct gab200_adam_segment {
   float* exp_avg;
   float* exp_avg_sq;
   int64_t n;
-  float lr;
+  double lr; /* hyper-parameters travel as double, like the Python floats torch forms its scalars from */
 } gab200_adam_segment;
-int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segments, int64_t step, float beta1,
-                         float beta2, float eps, void* stream);
+int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segments, int64_t step, double beta1,
+                         double beta2, double eps, void* stream);
 
 /* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
  * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */

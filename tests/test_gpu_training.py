@@ -55,7 +55,7 @@ def test_photometric_loss_matches_torch_restatement(shape):
     total, parts = g.photometric_loss(x, gt_u8, LAMBDA, return_parts=True)
     total.backward()
     xd = img.double().requires_grad_(True)
-    l1, ssim, tot = ol.photometric_torch(xd, gt_u8.double() / 255, LAMBDA)
+    l1, ssim, tot = ol.photometric_torch(xd, (gt_u8.float() / 255).double(), LAMBDA)   # fp32 division, as the loader does
     tot.backward()
     ref = torch.stack([l1, ssim, tot]).detach()
     assert (parts.double() - ref).abs().max().item() < 2e-6
