@@ -54,8 +54,8 @@ void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* gr
 // The reference evaluates SSIM with five grouped 11x11 convolutions and lets autograd run five more backwards
 // (utils/loss_utils.py:36-63, train.py:131-132): ~40 eager launches and ten (3,H,W) temporaries per step.  Here it is
 // two launches.  The Gaussian window is separable, so every 32x32 tile does an 11-tap horizontal pass out of a
-// 42x42 shared-memory tile and an 11-tap vertical pass out of the result, register-blocked (each thread produces four
-// outputs from 14 loaded values).
+// 42x42 shared-memory tile and an 11-tap vertical pass out of the result, register-blocked (a thread produces eight
+// horizontal outputs from 18 loaded values, four vertical outputs from 14).
 //
 //   ssim_stats_kernel : mu1, mu2, E[x^2], E[y^2], E[xy]  ->  the SSIM map (summed into loss[1]) and the three partial
 //                       derivatives  ds/dmu1, ds/dE[x^2], ds/dE[xy]  per pixel (12 B/px/channel of scratch);
@@ -74,92 +74,130 @@ constexpr int LT = 32;             // tile edge (outputs)
 constexpr int LHALO = 5;           // window_size // 2
 constexpr int LIN = LT + 2 * LHALO;
 constexpr int LTAPS = 2 * LHALO + 1;
-constexpr int LSEG = 4;            // outputs per thread per pass
+constexpr int LSEG_H = 8;          // outputs per thread, horizontal pass (168 work items per tile)
+constexpr int LLOAD_H = LSEG_H + LTAPS - 1;
+constexpr int LSEG = 4;            // outputs per thread, vertical pass (256 work items per tile)
 constexpr int LLOAD = LSEG + LTAPS - 1;
+constexpr int LROWS_PER_WARP = (LIN + 7) / 8;
 
 struct SsimWindow { float w[LTAPS]; };
 
-// value / 255 with a correctly rounded division: bit-identical to the reference's `torch.from_numpy(img) / 255.0`
-// (utils/general_utils.py:21-23); a multiply by 1/255 is off by one ulp for some codes and flips sign(x - y).
+// value / 255 with a correctly rounded division: bit-identical to the reference's CPU-side
+// `torch.from_numpy(np.array(img)) / 255.0` (utils/general_utils.py:21-23); a multiply by 1/255 is off by one ulp
+// for some codes and flips sign(x - y).  The tile kernels divide once per code into a 256-entry shared table.
 __device__ __forceinline__ float u8_unit(uint8_t v) { return __fdiv_rn((float)v, 255.f); }
-__device__ __forceinline__ float gt_value(const uint8_t* p, int64_t i) { return u8_unit(p[i]); }
-__device__ __forceinline__ float gt_value(const float* p, int64_t i) { return p[i]; }
+
+template <typename GT> struct GtFetch;
+template <> struct GtFetch<uint8_t> {
+  float tab[256];
+  __device__ __forceinline__ void init(int tid) {
+    tab[tid] = u8_unit((uint8_t)tid);  // blockDim.x == 256
+    __syncthreads();
+  }
+  __device__ __forceinline__ float operator()(const uint8_t* p, int64_t i) const { return tab[p[i]]; }
+};
+template <> struct GtFetch<float> {
+  __device__ __forceinline__ void init(int) {}
+  __device__ __forceinline__ float operator()(const float* p, int64_t i) const { return p[i]; }
+};
+
+// 11-tap pass over a register window: out[o] = sum_t w[t] v[o + t]
+template <int NOUT>
+__device__ __forceinline__ void taps(const SsimWindow& win, const float (&v)[NOUT + LTAPS - 1], float (&out)[NOUT]) {
+#pragma unroll
+  for (int o = 0; o < NOUT; o++) {
+    float a = 0.f;
+#pragma unroll
+    for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
+    out[o] = a;
+  }
+}
 
 template <typename GT>
 __global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const float* __restrict__ img,
-                                                         const GT* __restrict__ gt, SsimWindow win, float inv_n,
+                                                         const GT* __restrict__ gt, SsimWindow win,
                                                          float* __restrict__ maps, int64_t map_stride,
                                                          double* __restrict__ sums) {
   __shared__ float sx[LIN][LIN + 1], sy[LIN][LIN + 1];
   __shared__ float hs[5][LIN][LT + 1];
   __shared__ float part[2][8];
-  const int tid = threadIdx.x;
+  __shared__ GtFetch<GT> fetch;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
   const int64_t plane = (int64_t)blockIdx.z * H * W;
+  fetch.init(tid);
 
-  for (int i = tid; i < LIN * LIN; i += 256) {
-    const int r = i / LIN, c = i - r * LIN;
-    const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
-    float xv = 0.f, yv = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const int64_t o = plane + (int64_t)gy * W + gx;
-      xv = img[o];
-      yv = gt_value(gt, o);
+  // tile + halo, one row per warp per round (zero outside the image: conv2d's padding)
+#pragma unroll
+  for (int rr = 0; rr < LROWS_PER_WARP; rr++) {
+    const int r = wrp + rr * 8;
+    if (r < LIN) {
+      const int gy = y0 + r - LHALO;
+      const bool row_ok = gy >= 0 && gy < H;
+      const int64_t row = plane + (int64_t)gy * W;
+      const int gxa = x0 + lane - LHALO, gxb = gxa + 32;
+      float xa = 0.f, ya = 0.f, xb = 0.f, yb = 0.f;
+      if (row_ok && gxa >= 0 && gxa < W) {
+        xa = img[row + gxa];
+        ya = fetch(gt, row + gxa);
+      }
+      if (lane < LIN - 32 && row_ok && gxb < W) {
+        xb = img[row + gxb];
+        yb = fetch(gt, row + gxb);
+      }
+      sx[r][lane] = xa;
+      sy[r][lane] = ya;
+      if (lane < LIN - 32) {
+        sx[r][32 + lane] = xb;
+        sy[r][32 + lane] = yb;
+      }
     }
-    sx[r][c] = xv;
-    sy[r][c] = yv;
   }
   __syncthreads();
 
-  // horizontal pass: item = (row r, 4-column segment)
-  for (int item = tid; item < LIN * (LT / LSEG); item += 256) {
-    const int seg = item / LIN, r = item - seg * LIN;
-    const int c0 = seg * LSEG;
-    float xv[LLOAD], yv[LLOAD], xx[LLOAD], yy[LLOAD], xy[LLOAD];
+  // horizontal pass: item = (row r, 8-column segment); consecutive lanes take consecutive rows (stride 43: no conflicts)
+  if (tid < LIN * (LT / LSEG_H)) {
+    const int seg = tid / LIN, r = tid - seg * LIN;
+    const int c0 = seg * LSEG_H;
+    float xv[LLOAD_H], yv[LLOAD_H], pv[LLOAD_H], out[LSEG_H];
 #pragma unroll
-    for (int k = 0; k < LLOAD; k++) {
+    for (int k = 0; k < LLOAD_H; k++) {
       xv[k] = sx[r][c0 + k];
       yv[k] = sy[r][c0 + k];
-      xx[k] = xv[k] * xv[k];
-      yy[k] = yv[k] * yv[k];
-      xy[k] = xv[k] * yv[k];
     }
+    taps<LSEG_H>(win, xv, out);
 #pragma unroll
-    for (int o = 0; o < LSEG; o++) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    for (int o = 0; o < LSEG_H; o++) hs[0][r][c0 + o] = out[o];
+    taps<LSEG_H>(win, yv, out);
 #pragma unroll
-      for (int t = 0; t < LTAPS; t++) {
-        const float w = win.w[t];
-        a0 = fmaf(w, xv[o + t], a0);
-        a1 = fmaf(w, yv[o + t], a1);
-        a2 = fmaf(w, xx[o + t], a2);
-        a3 = fmaf(w, yy[o + t], a3);
-        a4 = fmaf(w, xy[o + t], a4);
-      }
-      hs[0][r][c0 + o] = a0;
-      hs[1][r][c0 + o] = a1;
-      hs[2][r][c0 + o] = a2;
-      hs[3][r][c0 + o] = a3;
-      hs[4][r][c0 + o] = a4;
-    }
+    for (int o = 0; o < LSEG_H; o++) hs[1][r][c0 + o] = out[o];
+#pragma unroll
+    for (int k = 0; k < LLOAD_H; k++) pv[k] = xv[k] * xv[k];
+    taps<LSEG_H>(win, pv, out);
+#pragma unroll
+    for (int o = 0; o < LSEG_H; o++) hs[2][r][c0 + o] = out[o];
+#pragma unroll
+    for (int k = 0; k < LLOAD_H; k++) pv[k] = yv[k] * yv[k];
+    taps<LSEG_H>(win, pv, out);
+#pragma unroll
+    for (int o = 0; o < LSEG_H; o++) hs[3][r][c0 + o] = out[o];
+#pragma unroll
+    for (int k = 0; k < LLOAD_H; k++) pv[k] = xv[k] * yv[k];
+    taps<LSEG_H>(win, pv, out);
+#pragma unroll
+    for (int o = 0; o < LSEG_H; o++) hs[4][r][c0 + o] = out[o];
   }
   __syncthreads();
 
   // vertical pass: thread = (column, group of 4 rows)
-  const int col = tid & 31, r0 = (tid >> 5) * LSEG;
+  const int col = lane, r0 = wrp * LSEG;
   float out[5][LSEG];
 #pragma unroll
   for (int q = 0; q < 5; q++) {
     float v[LLOAD];
 #pragma unroll
     for (int k = 0; k < LLOAD; k++) v[k] = hs[q][r0 + k][col];
-#pragma unroll
-    for (int o = 0; o < LSEG; o++) {
-      float a = 0.f;
-#pragma unroll
-      for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
-      out[q][o] = a;
-    }
+    taps<LSEG>(win, v, out[q]);
   }
   const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
   float l1_sum = 0.f, ssim_sum = 0.f;
@@ -176,7 +214,7 @@ __global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const flo
       const float inv_b = 1.f / (B1 * B2);
       const float s = A1 * A2 * inv_b;
       const float d_mu1 = 2.f * mu2 * (A2 - A1) * inv_b - 2.f * mu1 * s * (B2 - B1) * inv_b;
-      const float d_ex2 = -s / B2;
+      const float d_ex2 = -s * (B1 * inv_b);  // -s / B2
       const float d_exy = 2.f * A1 * inv_b;
       const int64_t o_px = plane + (int64_t)gy * W + gx;
       maps[o_px] = d_mu1;
@@ -191,9 +229,9 @@ __global__ void __launch_bounds__(256) ssim_stats_kernel(int H, int W, const flo
     l1_sum += __shfl_xor_sync(0xffffffffu, l1_sum, m);
     ssim_sum += __shfl_xor_sync(0xffffffffu, ssim_sum, m);
   }
-  if (col == 0) {
-    part[0][tid >> 5] = l1_sum;
-    part[1][tid >> 5] = ssim_sum;
+  if (lane == 0) {
+    part[0][wrp] = l1_sum;
+    part[1][wrp] = ssim_sum;
   }
   __syncthreads();
   if (tid < 2) {
@@ -212,57 +250,57 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(int H, int W, const floa
                                                         const double* __restrict__ sums, float* __restrict__ loss) {
   __shared__ float sm[3][LIN][LIN + 1];
   __shared__ float hs[3][LIN][LT + 1];
-  const int tid = threadIdx.x;
-  const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
-  const int64_t plane = (int64_t)blockIdx.z * H * W;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  // reverse of the stats kernel's block order: the maps it wrote last are the ones still in L2
+  const int x0 = (gridDim.x - 1 - blockIdx.x) * LT, y0 = (gridDim.y - 1 - blockIdx.y) * LT;
+  const int ch = gridDim.z - 1 - blockIdx.z;
+  const int64_t plane = (int64_t)ch * H * W;
 
-  for (int i = tid; i < LIN * LIN; i += 256) {
-    const int r = i / LIN, c = i - r * LIN;
-    const int gy = y0 + r - LHALO, gx = x0 + c - LHALO;
-    float a = 0.f, b = 0.f, d = 0.f;
-    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-      const int64_t o = plane + (int64_t)gy * W + gx;
-      a = maps[o];
-      b = maps[map_stride + o];
-      d = maps[2 * map_stride + o];
-    }
-    sm[0][r][c] = a;
-    sm[1][r][c] = b;
-    sm[2][r][c] = d;
-  }
-  __syncthreads();
-  for (int item = tid; item < LIN * (LT / LSEG); item += 256) {
-    const int seg = item / LIN, r = item - seg * LIN;
-    const int c0 = seg * LSEG;
 #pragma unroll
-    for (int q = 0; q < 3; q++) {
-      float v[LLOAD];
+  for (int rr = 0; rr < LROWS_PER_WARP; rr++) {
+    const int r = wrp + rr * 8;
+    if (r < LIN) {
+      const int gy = y0 + r - LHALO;
+      const bool row_ok = gy >= 0 && gy < H;
+      const int64_t row = plane + (int64_t)gy * W;
+      const int gxa = x0 + lane - LHALO, gxb = gxa + 32;
+      const bool oka = row_ok && gxa >= 0 && gxa < W, okb = lane < LIN - 32 && row_ok && gxb < W;
+      float a[3] = {0.f, 0.f, 0.f}, b[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int k = 0; k < LLOAD; k++) v[k] = sm[q][r][c0 + k];
+      for (int q = 0; q < 3; q++) {
+        if (oka) a[q] = maps[q * map_stride + row + gxa];
+        if (okb) b[q] = maps[q * map_stride + row + gxb];
+      }
 #pragma unroll
-      for (int o = 0; o < LSEG; o++) {
-        float a = 0.f;
-#pragma unroll
-        for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
-        hs[q][r][c0 + o] = a;
+      for (int q = 0; q < 3; q++) {
+        sm[q][r][lane] = a[q];
+        if (lane < LIN - 32) sm[q][r][32 + lane] = b[q];
       }
     }
   }
   __syncthreads();
-  const int col = tid & 31, r0 = (tid >> 5) * LSEG;
+  if (tid < LIN * (LT / LSEG_H)) {
+    const int seg = tid / LIN, r = tid - seg * LIN;
+    const int c0 = seg * LSEG_H;
+#pragma unroll
+    for (int q = 0; q < 3; q++) {
+      float v[LLOAD_H], out[LSEG_H];
+#pragma unroll
+      for (int k = 0; k < LLOAD_H; k++) v[k] = sm[q][r][c0 + k];
+      taps<LSEG_H>(win, v, out);
+#pragma unroll
+      for (int o = 0; o < LSEG_H; o++) hs[q][r][c0 + o] = out[o];
+    }
+  }
+  __syncthreads();
+  const int col = lane, r0 = wrp * LSEG;
   float out[3][LSEG];
 #pragma unroll
   for (int q = 0; q < 3; q++) {
     float v[LLOAD];
 #pragma unroll
     for (int k = 0; k < LLOAD; k++) v[k] = hs[q][r0 + k][col];
-#pragma unroll
-    for (int o = 0; o < LSEG; o++) {
-      float a = 0.f;
-#pragma unroll
-      for (int t = 0; t < LTAPS; t++) a = fmaf(win.w[t], v[o + t], a);
-      out[q][o] = a;
-    }
+    taps<LSEG>(win, v, out[q]);
   }
   const int gx = x0 + col;
   const float k_l1 = (1.f - lambda) * inv_n, k_ssim = -lambda * inv_n;
@@ -271,14 +309,16 @@ __global__ void __launch_bounds__(256) ssim_grad_kernel(int H, int W, const floa
     const int gy = y0 + r0 + o;
     if (gx < W && gy < H) {
       const int64_t o_px = plane + (int64_t)gy * W + gx;
-      const float x = img[o_px], y = gt_value(gt, o_px);
+      const float x = img[o_px];
+      float y;
+      if constexpr (sizeof(GT) == 1) y = u8_unit(gt[o_px]); else y = gt[o_px];
       const float d = x - y;
       const float sgn = d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
       const float dssim = out[0][o] + 2.f * x * out[1][o] + y * out[2][o];
       grad[o_px] = k_l1 * sgn + k_ssim * dssim;
     }
   }
-  // the stats kernel has completed (stream order): fold the two means into the total
+  // the stats kernel has completed (stream order): fold its two sums into the three reported means
   if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && tid == 0) {
     const double l1 = sums[0] * (double)inv_n, ssim = sums[1] * (double)inv_n;
     loss[0] = (float)l1;
@@ -305,7 +345,7 @@ static void launch_photometric_t(int C, int H, int W, const float* img, const GT
   const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
   double* sums = reinterpret_cast<double*>(scratch);  // [2], zeroed by the caller (api.cu); the maps follow
   float* maps = scratch + GAB_PHOTOMETRIC_SCRATCH_HEAD;
-  ssim_stats_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, maps, n, sums);
+  ssim_stats_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, maps, n, sums);
   count_launch();
   ssim_grad_kernel<GT><<<grid, 256, 0, stream>>>(H, W, img, gt, win, 1.0f / (float)n, lambda, maps, n, grad, sums, loss);
   count_launch();

@@ -50,20 +50,34 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamBatch b, float w1, float 
     // the gradient is usually a view into the fused backward's flat buffer: its offset need not be 16-byte aligned
     const bool g_vec = (b.vec4[s] & 2) != 0;
     const int64_t n4 = n >> 2;
-    for (int64_t i = t0; i < n4; i += stride) {
-      float4 P = reinterpret_cast<float4*>(p)[i];
-      float4 G;
-      if (g_vec) {
-        G = reinterpret_cast<const float4*>(g)[i];
-      } else {
-        G = make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
-      }
-      float4 M = reinterpret_cast<float4*>(m)[i];
-      float4 V = reinterpret_cast<float4*>(v)[i];
+    auto load_g = [&](int64_t i) {
+      return g_vec ? reinterpret_cast<const float4*>(g)[i] : make_float4(g[4 * i], g[4 * i + 1], g[4 * i + 2], g[4 * i + 3]);
+    };
+    auto update = [&](float4& P, const float4& G, float4& M, float4& V) {
       adam_one(P.x, G.x, M.x, V.x, w1, beta2, w2, inv_bc2_sqrt, eps, step_size);
       adam_one(P.y, G.y, M.y, V.y, w1, beta2, w2, inv_bc2_sqrt, eps, step_size);
       adam_one(P.z, G.z, M.z, V.z, w1, beta2, w2, inv_bc2_sqrt, eps, step_size);
       adam_one(P.w, G.w, M.w, V.w, w1, beta2, w2, inv_bc2_sqrt, eps, step_size);
+    };
+    int64_t i = t0;
+    for (; i + stride < n4; i += 2 * stride) {  // two independent 4 x 16 B load groups in flight per thread
+      const int64_t j = i + stride;
+      float4 P0 = reinterpret_cast<float4*>(p)[i], P1 = reinterpret_cast<float4*>(p)[j];
+      const float4 G0 = load_g(i), G1 = load_g(j);
+      float4 M0 = reinterpret_cast<float4*>(m)[i], M1 = reinterpret_cast<float4*>(m)[j];
+      float4 V0 = reinterpret_cast<float4*>(v)[i], V1 = reinterpret_cast<float4*>(v)[j];
+      update(P0, G0, M0, V0);
+      update(P1, G1, M1, V1);
+      reinterpret_cast<float4*>(p)[i] = P0; reinterpret_cast<float4*>(p)[j] = P1;
+      reinterpret_cast<float4*>(m)[i] = M0; reinterpret_cast<float4*>(m)[j] = M1;
+      reinterpret_cast<float4*>(v)[i] = V0; reinterpret_cast<float4*>(v)[j] = V1;
+    }
+    if (i < n4) {
+      float4 P = reinterpret_cast<float4*>(p)[i];
+      const float4 G = load_g(i);
+      float4 M = reinterpret_cast<float4*>(m)[i];
+      float4 V = reinterpret_cast<float4*>(v)[i];
+      update(P, G, M, V);
       reinterpret_cast<float4*>(p)[i] = P;
       reinterpret_cast<float4*>(m)[i] = M;
       reinterpret_cast<float4*>(v)[i] = V;
@@ -107,8 +121,8 @@ void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step
       b.p[i] = nullptr; b.g[i] = nullptr; b.m[i] = nullptr; b.v[i] = nullptr;
       b.n[i] = 0; b.step_size[i] = 0.f; b.vec4[i] = 0;
     }
-    // one float4 per thread for the longest group, capped at 8 waves of 148 SMs x 8 resident CTAs
-    int64_t blocks = (longest / 4 + 255) / 256;
+    // two float4 per thread for the longest group, capped at 8 waves of 148 SMs x 8 resident CTAs
+    int64_t blocks = (longest / 8 + 255) / 256;
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 8 * 8) blocks = 148 * 8 * 8;
     adam_kernel<<<dim3((unsigned)blocks, (unsigned)cnt), 256, 0, stream>>>(

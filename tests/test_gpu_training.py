@@ -27,7 +27,7 @@ def test_photometric_loss_matches_reference_vectors(case, gt_kind):
     img = torch.tensor(GOLD[f"{case}_image"], device="cuda").requires_grad_(True)
     gt = torch.tensor(GOLD[f"{case}_gt_u8"], device="cuda")
     if gt_kind == "f32":
-        gt = gt.float() / 255
+        gt = (gt.cpu().float() / 255).cuda()
     total, parts = g.photometric_loss(img, gt, LAMBDA, return_parts=True)
     total.backward()
     ref = GOLD[f"{case}_f64_scalars"]
@@ -55,7 +55,8 @@ def test_photometric_loss_matches_torch_restatement(shape):
     total, parts = g.photometric_loss(x, gt_u8, LAMBDA, return_parts=True)
     total.backward()
     xd = img.double().requires_grad_(True)
-    l1, ssim, tot = ol.photometric_torch(xd, (gt_u8.float() / 255).double(), LAMBDA)   # fp32 division, as the loader does
+    l1, ssim, tot = ol.photometric_torch(xd, (gt_u8.cpu().float() / 255).cuda().double(), LAMBDA)   # fp32 IEEE division on the CPU, as the
+    # reference's loader does (utils/general_utils.py:21-23); torch's CUDA `/ 255` multiplies by a reciprocal instead
     tot.backward()
     ref = torch.stack([l1, ssim, tot]).detach()
     assert (parts.double() - ref).abs().max().item() < 2e-6
@@ -79,7 +80,7 @@ def test_photometric_loss_properties():
     assert abs(float(t0.detach()) - float(l1.detach())) < 1e-6
     assert torch.equal(x.grad, x1.grad)
     # identical images: SSIM = 1, loss = 0, gradient ~ 0
-    q = (gt_u8.float() / 255).requires_grad_(True)
+    q = (gt_u8.cpu().float() / 255).cuda().requires_grad_(True)
     t, p = g.photometric_loss(q, gt_u8, LAMBDA, return_parts=True)
     t.backward()
     assert abs(float(p[1]) - 1.0) < 1e-6 and float(p[0]) == 0.0 and abs(float(t.detach())) < 1e-6
