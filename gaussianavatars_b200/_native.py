@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgaussianavatars_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 INPUT_ACTIVATED = 0
 INPUT_BOUND_RAW = 1
 
@@ -27,7 +27,7 @@ class ForwardArgs(C.Structure):
         ("sh_coeffs", C.c_int32), ("image_width", C.c_int32), ("image_height", C.c_int32),
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_backward", C.c_int32), ("binning_hint", C.c_int32),
-        ("exact_binning", C.c_int32),
+        ("exact_binning", C.c_int32), ("depth_hint_lo", C.c_uint32), ("depth_hint_hi", C.c_uint32),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
         ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
         ("cov3D_precomp", C.c_void_p), ("shs", C.c_void_p), ("sh_dc", C.c_void_p), ("sh_rest", C.c_void_p),
@@ -46,6 +46,8 @@ class FrameState(C.Structure):
         ("geom_bytes", C.c_size_t), ("binning_bytes", C.c_size_t), ("image_bytes", C.c_size_t),
         ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32), ("depth_bits", C.c_int32),
         ("depth_prefix", C.c_uint32), ("binning_capacity", C.c_int64),
+        ("depth_key_min", C.c_uint32), ("depth_key_max", C.c_uint32), ("depth_sort_path", C.c_int32),
+        ("reserved0", C.c_int32),
     ]
 
 

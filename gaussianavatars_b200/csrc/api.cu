@@ -4,6 +4,7 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <vector>
@@ -47,8 +48,16 @@ struct GeomView {
   float* face_scratch;  // [P,13] per-splat face-frame gradients (CSR route of the fused backward)
   void* scan_temp;
   size_t scan_temp_bytes;
+  DepthBuckets buckets;  // bucket-sort bookkeeping (counts | tiles | meta contiguous: one memset)
+  size_t bucket_clear_bytes;
   size_t bytes;
 };
+// buckets for the per-splat depth sort: ~32 splats each, a power of two in [256, 8192]
+static uint32_t depth_bucket_count(int P) {
+  uint32_t nb = 256;
+  while (nb < 8192 && (int64_t)nb * 32 < P) nb <<= 1;
+  return nb;
+}
 static GeomView carve_geom(void* base, int P, bool need_backward) {
   GeomView g;
   Carver c(base);
@@ -67,6 +76,21 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   g.face_scratch = need_backward ? c.take<float>((size_t)P * GAB_FACE_GRAD_STRIDE) : nullptr;
   g.scan_temp_bytes = scan_temp_bytes(P);
   g.scan_temp = c.take<char>(g.scan_temp_bytes);
+  {
+    DepthBuckets& d = g.buckets;
+    d.nb = depth_bucket_count(P);
+    uint32_t* head = c.take<uint32_t>((size_t)2 * d.nb + GAB_DEPTH_META_WORDS);
+    d.counts = head;
+    d.tiles = head ? head + d.nb : nullptr;
+    d.meta = head ? head + 2 * d.nb : nullptr;
+    g.bucket_clear_bytes = sizeof(uint32_t) * ((size_t)2 * d.nb + GAB_DEPTH_META_WORDS);
+    d.start = c.take<uint32_t>((size_t)d.nb);
+    d.tile_base = c.take<uint32_t>((size_t)d.nb);
+    d.rank = c.take<uint32_t>((size_t)P);
+    d.lo = d.hi = 0;
+    d.scale = 0.f;
+    d.enabled = 0;
+  }
   g.bytes = c.bytes();
   return g;
 }
@@ -304,13 +328,35 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   size_t bin_bytes_have = 0;
   bool ranges_cleared = false;
   int64_t mask_cleared_for = -1;
+  const uint32_t* order_count = nullptr;  // device count of listed splats (bucket path), else all P are listed
+  bool bucket_path = false;
   if (P > 0) {
     {
+      static const bool no_bucket = getenv("GAB200_DEPTH_SORT") != nullptr && strcmp(getenv("GAB200_DEPTH_SORT"), "radix") == 0;
+      DepthBuckets& d = g.buckets;
+      if (a->depth_hint_hi > a->depth_hint_lo && !no_bucket) {
+        d.lo = a->depth_hint_lo;
+        d.hi = a->depth_hint_hi;
+        d.scale = (float)((double)d.nb / ((double)(d.hi - d.lo) + 1.0));
+        d.enabled = 1;
+        bucket_path = true;
+      }
+      GAB_CUDA(cudaMemsetAsync(d.counts, 0, g.bucket_clear_bytes, stream));
+    }
+    {
       StageScope sc(GAB200_STAGE_PREPROCESS, stream);
-      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], stream);
+      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], g.buckets,
+                        stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
-    {
+    if (!t_slot.ok()) return GAB200_ERR_CUDA;
+    if (bucket_path) {
+      // per-splat depth order + emission offsets as a bucket sort over the hinted key range -- see binning.cu
+      StageScope sc(GAB200_STAGE_SCAN, stream);
+      launch_depth_bucket_sort(P, g.buckets, g.depth_keys[0], g.tiles_touched, g.depth_keys[1], g.ids[1], g.offsets, stream);
+      selA = 1;
+      order_count = g.buckets.meta + 3;
+    } else {
       // stage A of the key sort (per splat, by depth) + emission offsets in depth order  -- see binning.cu
       StageScope sc(GAB200_STAGE_SCAN, stream);
       GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], P, 32,
@@ -318,8 +364,11 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
       GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[selA], g.tiles_touched, g.offsets, P, stream));
     }
     GAB_STAGE_CHECK(dbg, stream);
-    if (!t_slot.ok()) return GAB200_ERR_CUDA;
-    GAB_CUDA(cudaMemcpyAsync(t_slot.host, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    // read back: host[0..7] = meta (min/max key; N, M, overflow on the bucket path), host[8] = N of the radix path
+    GAB_CUDA(cudaMemcpyAsync(t_slot.host, g.buckets.meta, sizeof(uint32_t) * GAB_DEPTH_META_WORDS,
+                             cudaMemcpyDeviceToHost, stream));
+    if (!bucket_path)
+      GAB_CUDA(cudaMemcpyAsync(t_slot.host + 8, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
     GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
     // speculative binning allocation while the GPU is still busy with preprocess + scan
     t_sync0 = now_us();
@@ -345,7 +394,26 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
       if (q == cudaSuccess) break;
       if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
     }
-    N = (int64_t)t_slot.host[0];
+    st->depth_key_min = ~t_slot.host[0];
+    st->depth_key_max = t_slot.host[1];
+    st->depth_sort_path = bucket_path ? 1 : 0;
+    N = (int64_t)(bucket_path ? t_slot.host[2] : t_slot.host[8]);
+    if (bucket_path && t_slot.host[4] != 0) {
+      // a bucket overflowed its shared-memory budget (the hint did not fit this frame): redo on the radix path
+      st->depth_sort_path = 2;
+      GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], P, 32,
+                        &selA, stream));
+      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[selA], g.tiles_touched, g.offsets, P, stream));
+      GAB_CUDA(cudaMemcpyAsync(t_slot.host + 8, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+      GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
+      for (;;) {
+        const cudaError_t q = cudaEventQuery(t_slot.ev);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
+      }
+      N = (int64_t)t_slot.host[8];
+      order_count = nullptr;
+    }
     t_sync1 = now_us();
   }
   st->num_rendered = N;
@@ -373,8 +441,8 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (N > 0) {
     {
       StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.ids[selA], g.offsets, bv.keys[0], bv.vals[0], a->exact_binning,
-                       stream);
+      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.ids[selA], g.offsets, order_count, bv.keys[0], bv.vals[0],
+                       a->exact_binning, stream);
     }
     GAB_STAGE_CHECK(dbg, stream);
     {

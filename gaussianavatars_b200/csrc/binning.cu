@@ -9,6 +9,21 @@
 //   stage B  cub::DeviceRadixSort::SortPairs (u32 tile id, u32 splat id), bits [0, bits(tiles))        [2 passes x 8 B x N]
 // Stable passes compose: the result is exactly the reference's order (ties: ascending splat id), tested bit for bit,
 // while the N-sized traffic drops from 6 passes x 12 B to 2 passes x 8 B.
+//
+// Stage A + scan at P ~ 1e5 are latency, not bandwidth: cub's onesweep is 6 launches of ~12 CTAs chained by
+// decoupled look-back, the scan 2 more (77 us together at 100k splats).  When the caller passes the previous frame's
+// depth-key range (gab200_forward_args.depth_hint_*), stage A + scan run as a BUCKET SORT instead (preprocess.cu):
+//   preprocess_kernel    bucket = floor((key - lo) * nb / (hi - lo + 1)) clamped to [0, nb) -- monotonic in the key;
+//                        atomicAdd on the bucket's splat counter returns the splat's arrival rank; a second counter
+//                        sums the bucket's instances.  (~32 splats per bucket, nb a power of two <= 8192.)
+//   depth_scatter_kernel every CTA rebuilds the exclusive prefix of the nb counters in shared memory and drops
+//                        (key, id) at start[bucket] + rank; CTA 0 publishes the prefixes, N and M.
+//   depth_bucket_kernel  one CTA per bucket ranks its (key << 32 | id) pairs by counting in shared memory and writes
+//                        ids in (key, id) order -- exactly what a stable sort by key of ids 0..P-1 gives -- plus the
+//                        running instance counts (the scan), offset by the bucket's base.
+// Keys outside [lo, hi] share the end buckets (order still right); a bucket that outgrows shared memory (2048 splats)
+// raises a flag that the host reads with N, and the frame is redone with stage A + scan above.  Same output either
+// way, bit for bit (tests/test_gpu_depth_sort.py).
 #include <cub/cub.cuh>
 #include <cub/iterator/transform_input_iterator.cuh>
 

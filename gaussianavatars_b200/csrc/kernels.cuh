@@ -69,13 +69,42 @@ struct TileSpan {
 };
 
 // ---- launchers (each counts its launches) ----
+// Per-splat depth sort as a bucket sort (binning.cu header): bookkeeping arrays in the geometry buffer.
+#define GAB_DEPTH_BUCKET_CAP 2048   // splats one bucket may hold before the frame falls back to the radix path
+#define GAB_DEPTH_META_WORDS 8      // [0] ~min key, [1] max key, [2] N, [3] M (splats with instances), [4] overflow flag
+struct DepthBuckets {
+  uint32_t* counts;     // [nb] splats per bucket           } zeroed together with meta before preprocess
+  uint32_t* tiles;      // [nb] instances per bucket        }
+  uint32_t* meta;       // [GAB_DEPTH_META_WORDS]           }
+  uint32_t* start;      // [nb] exclusive prefix of counts
+  uint32_t* tile_base;  // [nb] exclusive prefix of tiles
+  uint32_t* rank;       // [P]  arrival rank of the splat inside its bucket
+  uint32_t nb;          // buckets (power of two)
+  uint32_t lo, hi;      // hinted key range; keys outside are clamped to the end buckets (order is preserved)
+  float scale;          // nb / (hi - lo + 1)
+  int enabled;          // 0: only meta[0..1] (min/max key) are maintained
+};
+// Monotonic non-decreasing in `key` (u32->f32 conversion, multiply by a positive constant and truncation all are),
+// which is all the bucket sort needs.  Evaluated in preprocess.cu only (one translation unit, one set of flags).
+__device__ __forceinline__ uint32_t depth_bucket(uint32_t key, const DepthBuckets& d) {
+  if (key <= d.lo) return 0u;
+  if (key >= d.hi) return d.nb - 1u;
+  const uint32_t b = (uint32_t)(__uint2float_rz(key - d.lo) * d.scale);
+  return b < d.nb ? b : d.nb - 1u;
+}
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, cudaStream_t stream);
+                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, const DepthBuckets& buckets,
+                       cudaStream_t stream);
+// depth_keys [P] (by splat) -> sorted_ids [M] in (key, id) order and offsets [M] = inclusive instance counts
+void launch_depth_bucket_sort(int P, const DepthBuckets& buckets, const uint32_t* depth_keys,
+                              const uint32_t* tiles_touched, uint32_t* scratch_keys, uint32_t* sorted_ids,
+                              uint32_t* offsets, cudaStream_t stream);
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
-                      const uint32_t* offsets, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
+                      const uint32_t* offsets, const uint32_t* order_count, uint32_t* keys, uint32_t* vals,
+                      int exact_binning, cudaStream_t stream);
 void launch_tile_ranges(int64_t N, const uint32_t* keys, uint2* ranges, cudaStream_t stream);
 void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
                         cudaStream_t stream);

@@ -35,7 +35,8 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
                                                             uint32_t* __restrict__ tiles_touched,
                                                             uint8_t* __restrict__ clamped,
                                                             uint32_t* __restrict__ depth_keys,
-                                                            uint32_t* __restrict__ ids, int exact_binning) {
+                                                            uint32_t* __restrict__ ids, int exact_binning,
+                                                            DepthBuckets bk) {
   __shared__ Camera cam;
   __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   stage_camera(a, cam);
@@ -205,8 +206,25 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     }
   }
   // stage-A sort input: the fp32 depth bit pattern (splats that emit nothing go last), value = splat id
-  depth_keys[i] = tiles_out ? __float_as_uint(depth_out) : 0xffffffffu;
+  const uint32_t dkey = tiles_out ? __float_as_uint(depth_out) : 0xffffffffu;
+  depth_keys[i] = dkey;
   ids[i] = (uint32_t)i;
+  {
+    // key range of this frame (the caller's hint for the next one) and, with a hint, the bucket histogram + the
+    // splat's arrival rank in its bucket (binning.cu header)
+    const unsigned live = __activemask();
+    const uint32_t kmin = __reduce_min_sync(live, dkey);
+    const uint32_t kmax = __reduce_max_sync(live, tiles_out ? dkey : 0u);
+    if ((threadIdx.x & 31) == (__ffs(live) - 1) && kmin != 0xffffffffu) {
+      atomicMax(bk.meta + 0, ~kmin);
+      atomicMax(bk.meta + 1, kmax);
+    }
+    if (bk.enabled && tiles_out) {
+      const uint32_t b = depth_bucket(dkey, bk);
+      bk.rank[i] = atomicAdd(bk.counts + b, 1u);
+      atomicAdd(bk.tiles + b, tiles_out);
+    }
+  }
   rec[i] = out;
   SplatAux ax;
   ax.depth = depth_out; ax.radius = radius_out; ax.tiles = tiles_out; ax.pad = 0;
@@ -217,13 +235,157 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
 }
 
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
-                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, cudaStream_t stream) {
+                       uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, const DepthBuckets& buckets,
+                       cudaStream_t stream) {
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning);
+    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning, buckets);
   else
-    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning);
+    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning, buckets);
+  count_launch();
+}
+
+// =====================================================================================================
+// Per-splat depth sort as a bucket sort (design: binning.cu header).  preprocess_kernel has already counted the
+// splats and instances of every bucket and given each splat its arrival rank.
+//   depth_scatter_kernel : every CTA scans the bucket counts in shared memory, then scatters (key, id) of its
+//                          splats to start[bucket] + rank.  CTA 0 also publishes the two exclusive prefixes and
+//                          {N, M, overflow} in meta.
+//   depth_bucket_kernel  : one CTA per bucket: ranks the bucket's (key, id) pairs by counting (they fit in shared
+//                          memory; ~25 of them on average), writes the ids in (key, id) order -- the order of a
+//                          stable sort by key of ids 0..P-1 -- and the running instance counts.
+// =====================================================================================================
+constexpr int DS_NT = 256;
+
+// exclusive prefix sum of s[0..n) in place (n a multiple of DS_NT); returns the total to every thread
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* s, int n, uint32_t* warp_tot) {
+  const int tid = threadIdx.x, per = n / DS_NT;
+  uint32_t local = 0;
+  for (int k = 0; k < per; k++) local += s[tid * per + k];
+  uint32_t incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((tid & 31) >= d) incl += nb;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t base = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < DS_NT / 32; w++) {
+    const uint32_t t = warp_tot[w];
+    if (w < (tid >> 5)) base += t;
+    total += t;
+  }
+  uint32_t run = base + incl - local;
+  for (int k = 0; k < per; k++) {
+    const uint32_t v = s[tid * per + k];
+    s[tid * per + k] = run;
+    run += v;
+  }
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(DS_NT) depth_scatter_kernel(int P, DepthBuckets bk,
+                                                              const uint32_t* __restrict__ depth_keys,
+                                                              uint32_t* __restrict__ out_keys,
+                                                              uint32_t* __restrict__ out_ids) {
+  extern __shared__ uint32_t s_start[];  // [nb]
+  __shared__ uint32_t warp_tot[DS_NT / 32];
+  __shared__ uint32_t s_flag;
+  const int tid = threadIdx.x, nb = (int)bk.nb;
+  if (tid == 0) s_flag = 0;
+  uint32_t over = 0;
+  for (int b = tid; b < nb; b += DS_NT) {
+    const uint32_t c = bk.counts[b];
+    s_start[b] = c;
+    over |= (c > GAB_DEPTH_BUCKET_CAP) ? 1u : 0u;
+  }
+  __syncthreads();
+  const uint32_t M = block_exclusive_scan(s_start, nb, warp_tot);
+  if (blockIdx.x == 0) {
+    if (over) atomicOr(&s_flag, 1u);
+    for (int b = tid; b < nb; b += DS_NT) bk.start[b] = s_start[b];
+  }
+  const int i = blockIdx.x * DS_NT + tid;
+  if (i < P) {
+    const uint32_t key = depth_keys[i];
+    if (key != 0xffffffffu) {
+      const uint32_t pos = s_start[depth_bucket(key, bk)] + bk.rank[i];
+      out_keys[pos] = key;
+      out_ids[pos] = (uint32_t)i;
+    }
+  }
+  if (blockIdx.x == 0) {  // second scan (instances per bucket), reusing the shared array
+    __syncthreads();
+    for (int b = tid; b < nb; b += DS_NT) s_start[b] = bk.tiles[b];
+    __syncthreads();
+    const uint32_t N = block_exclusive_scan(s_start, nb, warp_tot);
+    for (int b = tid; b < nb; b += DS_NT) bk.tile_base[b] = s_start[b];
+    if (tid == 0) {
+      bk.meta[2] = N;
+      bk.meta[3] = M;
+      bk.meta[4] = s_flag;
+    }
+  }
+}
+
+constexpr int DB_NT = 128;
+__global__ void __launch_bounds__(DB_NT) depth_bucket_kernel(DepthBuckets bk, const uint32_t* __restrict__ keys,
+                                                             uint32_t* __restrict__ ids_inout,
+                                                             const uint32_t* __restrict__ tiles_touched,
+                                                             uint32_t* __restrict__ offsets) {
+  __shared__ unsigned long long comp[GAB_DEPTH_BUCKET_CAP];
+  __shared__ uint32_t st[GAB_DEPTH_BUCKET_CAP];
+  __shared__ uint32_t warp_tot[DB_NT / 32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = (int)bk.counts[b];
+  if (n == 0 || n > GAB_DEPTH_BUCKET_CAP) return;  // overflow: the host redoes the frame on the radix path
+  const uint32_t start = bk.start[b], tbase = bk.tile_base[b];
+  for (int j = tid; j < n; j += DB_NT)
+    comp[j] = ((unsigned long long)keys[start + j] << 32) | (unsigned long long)ids_inout[start + j];
+  __syncthreads();
+  for (int t = tid; t < n; t += DB_NT) {
+    const unsigned long long c = comp[t];
+    int r = 0;
+    for (int j = 0; j < n; j++) r += comp[j] < c ? 1 : 0;  // broadcast reads; ids are distinct -> ranks are too
+    const uint32_t id = (uint32_t)c;
+    ids_inout[start + r] = id;  // in place: the bucket's inputs are all in shared memory by now
+    st[r] = tiles_touched[id];
+  }
+  __syncthreads();
+  // inclusive running instance count in sorted order
+  const int per = (n + DB_NT - 1) / DB_NT;
+  const int j0 = min(tid * per, n), j1 = min(j0 + per, n);
+  uint32_t local = 0;
+  for (int j = j0; j < j1; j++) local += st[j];
+  uint32_t incl = local;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t nbv = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((tid & 31) >= d) incl += nbv;
+  }
+  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  __syncthreads();
+  uint32_t run = tbase + incl - local;
+#pragma unroll
+  for (int w = 0; w < DB_NT / 32; w++)
+    if (w < (tid >> 5)) run += warp_tot[w];
+  for (int j = j0; j < j1; j++) {
+    run += st[j];
+    offsets[start + j] = run;
+  }
+}
+
+void launch_depth_bucket_sort(int P, const DepthBuckets& bk, const uint32_t* depth_keys, const uint32_t* tiles_touched,
+                              uint32_t* scratch_keys, uint32_t* sorted_ids, uint32_t* offsets, cudaStream_t stream) {
+  if (P <= 0) return;
+  depth_scatter_kernel<<<(P + DS_NT - 1) / DS_NT, DS_NT, bk.nb * sizeof(uint32_t), stream>>>(P, bk, depth_keys,
+                                                                                              scratch_keys, sorted_ids);
+  count_launch();
+  depth_bucket_kernel<<<bk.nb, DB_NT, 0, stream>>>(bk, scratch_keys, sorted_ids, tiles_touched, offsets);
   count_launch();
 }
 
@@ -294,6 +456,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
                                                         const SplatAux* __restrict__ aux,
                                                         const uint32_t* __restrict__ order,
                                                         const uint32_t* __restrict__ offsets,
+                                                        const uint32_t* __restrict__ order_count,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                         int exact_binning) {
   constexpr unsigned FULL = 0xffffffffu;
@@ -303,7 +466,9 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   float px = 0.f, py = 0.f, cA = 0.f, cB = 0.f, cC = 0.f, op = 0.f;
   int radius = 0;
   uint32_t ntiles = 0, off = 0, i = 0;
-  if (slot < P) {
+  // bucket-sorted frames list only the M splats that emit instances; radix-sorted frames list all P (culled last)
+  const int listed = order_count != nullptr ? (int)*order_count : P;
+  if (slot < listed) {
     i = order[slot];
     const SplatAux ax = aux[i];
     ntiles = ax.tiles;
@@ -388,11 +553,12 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
 }
 
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
-                      const uint32_t* offsets, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
+                      const uint32_t* offsets, const uint32_t* order_count, uint32_t* keys, uint32_t* vals,
+                      int exact_binning, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, keys, vals, exact_binning);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, order_count, keys, vals, exact_binning);
   count_launch();
 }
 

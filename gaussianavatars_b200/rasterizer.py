@@ -79,6 +79,7 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
     a.need_backward = int(need_backward)
     a.exact_binning = int(_EXACT_BINNING)
     a.binning_hint = _binning_hint.get((device, a.image_width, a.image_height, P), 0)
+    a.depth_hint_lo, a.depth_hint_hi = _depth_hint.get((device, a.image_width, a.image_height, P), (0, 0))
     cams = (_cam(rs.bg, "bg", device), _cam(rs.viewmatrix, "viewmatrix", device),
             _cam(rs.projmatrix, "projmatrix", device), _cam(rs.campos, "campos", device))
     a.bg, a.viewmatrix, a.projmatrix, a.campos = (t.data_ptr() for t in cams)
@@ -88,6 +89,15 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
 _KEEP_LAST = False
 _last = None
 _binning_hint = {}  # (device, W, H, P) -> expected instance count (last N * 1.25): see gab200_forward_args.binning_hint
+_depth_hint = {}    # (device, W, H, P) -> (lo, hi) depth-key range of the last frame, widened: gab200_forward_args.depth_hint_*
+
+
+def _widen_depth_range(kmin: int, kmax: int):
+    """The last frame's visible depth-key range plus 1/8 of its width either side (keys are fp32 bit patterns of
+    positive depths: monotonic, so a range in key space is a range in depth).  A frame that falls outside is still
+    sorted correctly -- outliers share the two end buckets -- so the margin only has to keep that rare."""
+    pad = max((kmax - kmin) // 8, 1 << 12)
+    return max(kmin - pad, 1), min(kmax + pad, 0xFFFFFFFE)
 
 
 def keep_last_state(flag: bool):
@@ -128,6 +138,8 @@ def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
         n = N.lib().gab200_forward(C.byref(a), C.byref(st), C.c_void_p(stream))
     N.check(n, "gab200_forward")
     _binning_hint[(device, a.image_width, a.image_height, P)] = min(int(n * 1.25) + 4096, 2**31 - 1)
+    if st.depth_key_min <= st.depth_key_max:
+        _depth_hint[(device, a.image_width, a.image_height, P)] = _widen_depth_range(st.depth_key_min, st.depth_key_max)
     if _KEEP_LAST:
         global _last
         # pooled (inference) scratch stays valid until the next no_grad forward on this device

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GAB200_ABI_VERSION 1
+#define GAB200_ABI_VERSION 2
 
 typedef enum gab200_status {
   GAB200_OK = 0,
@@ -74,6 +74,12 @@ typedef struct gab200_forward_args {
   int32_t exact_binning;   /* 1: emit the reference's full 3-sigma bounding-square instance list;
                               0: additionally drop (splat,tile) pairs that provably contribute nothing
                                  (alpha < 1/255 over the whole tile): image/gradients unchanged */
+  uint32_t depth_hint_lo;  /* expected range of the visible splats' depth keys (fp32 bit patterns of view-space z), e.g.
+                              the previous frame's gab200_frame_state.depth_key_min/max widened a little; hi <= lo = unknown.
+                              With a hint the per-splat depth sort runs as a bucket sort (3 small launches) instead of
+                              cub::DeviceRadixSort + DeviceScan (8 launches); the result is the same bit for bit, and a
+                              hint that turns out wrong only costs the time of the radix path on top. */
+  uint32_t depth_hint_hi;
 
   /* camera block */
   const float* bg;         /* [3] */
@@ -124,6 +130,10 @@ typedef struct gab200_frame_state {
   uint32_t depth_prefix;      /* reserved (0) */
   int64_t binning_capacity;   /* instances the binning buffer was carved for (>= num_rendered; = binning_hint when the
                                  speculative allocation was large enough) */
+  uint32_t depth_key_min;     /* smallest / largest depth key among the splats that emitted instances (min > max: none) */
+  uint32_t depth_key_max;
+  int32_t depth_sort_path;    /* 0: radix sort (no hint); 1: bucket sort; 2: bucket sort overflowed, radix sort redone */
+  int32_t reserved0;
 } gab200_frame_state;
 
 /* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
