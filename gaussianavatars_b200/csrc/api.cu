@@ -52,10 +52,10 @@ struct GeomView {
   size_t bucket_clear_bytes;
   size_t bytes;
 };
-// buckets for the per-splat depth sort: ~32 splats each, a power of two in [256, 8192]
+// buckets for the per-splat depth sort: 32..64 splats each, a power of two in [256, 8192]
 static uint32_t depth_bucket_count(int P) {
   uint32_t nb = 256;
-  while (nb < 8192 && (int64_t)nb * 32 < P) nb <<= 1;
+  while (nb < 8192 && (int64_t)nb * 64 < P) nb <<= 1;
   return nb;
 }
 static GeomView carve_geom(void* base, int P, bool need_backward) {

@@ -15,7 +15,7 @@
 // depth-key range (gab200_forward_args.depth_hint_*), stage A + scan run as a BUCKET SORT instead (preprocess.cu):
 //   preprocess_kernel    bucket = floor((key - lo) * nb / (hi - lo + 1)) clamped to [0, nb) -- monotonic in the key;
 //                        atomicAdd on the bucket's splat counter returns the splat's arrival rank; a second counter
-//                        sums the bucket's instances.  (~32 splats per bucket, nb a power of two <= 8192.)
+//                        sums the bucket's instances.  (32..64 splats per bucket, nb a power of two <= 8192.)
 //   depth_scatter_kernel every CTA rebuilds the exclusive prefix of the nb counters in shared memory and drops
 //                        (key, id) at start[bucket] + rank; CTA 0 publishes the prefixes, N and M.
 //   depth_bucket_kernel  one CTA per bucket ranks its (key << 32 | id) pairs by counting in shared memory and writes

@@ -258,32 +258,35 @@ void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* au
 // =====================================================================================================
 constexpr int DS_NT = 256;
 
-// exclusive prefix sum of s[0..n) in place (n a multiple of DS_NT); returns the total to every thread
+// Exclusive prefix sum of s[0..n) in place (n a multiple of DS_NT); returns the total to every thread.  Warp w owns
+// the contiguous slice [w n/8, (w+1) n/8) and walks it 32 elements at a time (lane = element: no bank conflicts --
+// a thread-owns-a-run layout is a 32-way conflict on every access and cost 50 us at 8192 buckets).
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* s, int n, uint32_t* warp_tot) {
-  const int tid = threadIdx.x, per = n / DS_NT;
-  uint32_t local = 0;
-  for (int k = 0; k < per; k++) local += s[tid * per + k];
-  uint32_t incl = local;
+  constexpr unsigned FULL = 0xffffffffu;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int slice = n / (DS_NT / 32);
+  uint32_t carry = 0;
+  for (int base = w * slice; base < (w + 1) * slice; base += 32) {
+    const uint32_t v = s[base + lane];
+    uint32_t incl = v;
 #pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((tid & 31) >= d) incl += nb;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t up = __shfl_up_sync(FULL, incl, d);
+      if (lane >= d) incl += up;
+    }
+    s[base + lane] = carry + incl - v;
+    carry += __shfl_sync(FULL, incl, 31);
   }
-  if ((tid & 31) == 31) warp_tot[tid >> 5] = incl;
+  if (lane == 0) warp_tot[w] = carry;
   __syncthreads();
-  uint32_t base = 0, total = 0;
+  uint32_t wbase = 0, total = 0;
 #pragma unroll
-  for (int w = 0; w < DS_NT / 32; w++) {
-    const uint32_t t = warp_tot[w];
-    if (w < (tid >> 5)) base += t;
+  for (int k = 0; k < DS_NT / 32; k++) {
+    const uint32_t t = warp_tot[k];
+    if (k < w) wbase += t;
     total += t;
   }
-  uint32_t run = base + incl - local;
-  for (int k = 0; k < per; k++) {
-    const uint32_t v = s[tid * per + k];
-    s[tid * per + k] = run;
-    run += v;
-  }
+  for (int base = w * slice; base < (w + 1) * slice; base += 32) s[base + lane] += wbase;
   __syncthreads();
   return total;
 }

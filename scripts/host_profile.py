@@ -43,6 +43,19 @@ ht = N.host_times(True)
 print(json.dumps({"W": W, "H": H, "P": P, "us_per_step_total": round(t_all / K * 1e6, 1), "us_per_step_host_enqueue": round(t_enq / K * 1e6, 1),
                   "host_us_by_section": {k: round(v / K * 1e6, 1) for k, v in sec.items()},
                   "inside_gab200_forward_us": ht}), flush=True)
+# per-stage GPU time of the same step (library events on: perturbs the step a little) and which depth-sort path ran
+from gaussianavatars_b200 import rasterizer as R
+N.stage_timing(True); N.stage_times(True)
+for i in range(48): step(i, False)
+st_ = N.stage_times(True); N.stage_timing(False)
+R.keep_last_state(True); step(0, False); torch.cuda.synchronize()
+print(json.dumps({"gpu_stage_us": {k: round(v[0] / max(v[1], 1) * 1e3, 1) for k, v in st_.items()},
+                  "gpu_stage_sum_us": round(sum(v[0] / max(v[1], 1) for v in st_.values()) * 1e3, 1),
+                  "depth_sort_path": int(R._last[1].depth_sort_path), "N": int(R._last[1].num_rendered),
+                  "depth_sort_env": os.environ.get("GAB200_DEPTH_SORT", "default")}), flush=True)
+R.keep_last_state(False)
+if os.environ.get("NOPROF") == "1":
+    sys.exit(0)
 pr = cProfile.Profile(); pr.enable()
 for i in range(K): step(i, False)
 pr.disable(); torch.cuda.synchronize()
