@@ -8,7 +8,8 @@ from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rast
                          bind_activate, set_exact_binning, face_frame, l1_loss_u8)
 from .renderer import render, render_bound
 from .training import photometric_loss, Adam
+from .io import load_ply, save_ply
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "rasterize_bound",
            "bind_activate", "set_exact_binning", "face_frame", "l1_loss_u8", "render", "render_bound",
-           "photometric_loss", "Adam"]
+           "photometric_loss", "Adam", "load_ply", "save_ply"]

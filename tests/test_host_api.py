@@ -183,3 +183,20 @@ def test_adam_keeps_the_torch_optimizer_surface():
     p.grad = torch.ones_like(p)
     with pytest.raises(RuntimeError, match="no CPU or eager fallback"):
         opt.step()
+
+
+def test_depth_hint_widening_stays_a_valid_key_range():
+    """The hint handed to gab200_forward_args.depth_hint_* : ordered, inside (0, 0xFFFFFFFF), wider than the frame."""
+    import struct
+    from gaussianavatars_b200 import rasterizer as R
+
+    def key(z):
+        return struct.unpack("<I", struct.pack("<f", z))[0]
+
+    for zmin, zmax in [(0.73, 1.31), (0.2000001, 0.2000002), (5.0, 5.0), (1e-3, 1e30), (3.0e38, 3.4e38)]:
+        lo, hi = R._widen_depth_range(key(zmin), key(zmax))
+        assert 0 < lo <= key(zmin) <= key(zmax) <= hi <= 0xFFFFFFFE
+        assert hi > lo                                   # hi <= lo would mean "no hint" to the library
+    lo, hi = R._widen_depth_range(key(0.73), key(1.31))
+    span = key(1.31) - key(0.73)
+    assert key(0.73) - lo == span // 8 and hi - key(1.31) == span // 8
