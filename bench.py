@@ -440,9 +440,14 @@ def main():
     peak = float(peaks.get("hbm_gbs", 6650.0))
     achieved = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9
     traffic = None
+    secondary = None  # the path is not HBM-bound at this size: report the limiter ncu names beside the roofline
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
         traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
+        if tj.get(dom, {}).get("issue_active_per_cycle") is not None:
+            secondary = {"bound": "issue slots", "issue_active_per_cycle": tj[dom]["issue_active_per_cycle"],
+                         "warps_active_per_scheduler": tj[dom].get("warps_active_per_scheduler"),
+                         "registers": tj[dom].get("registers"), "source": tj[dom].get("source")}
     except Exception:
         pass
     frame_alg = sum(alg.values())
@@ -463,7 +468,7 @@ def main():
         "clocks": clk.summary(),
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak,
                      "peak_source": "measured" if peaks else "fallback", "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "algorithmic_bytes_per_launch": alg[dom],
+                     "traffic": traffic, "secondary": secondary, "algorithmic_bytes_per_launch": alg[dom],
                      "avg_launch_ms": stage_ms[dom],
                      "frame": {"algorithmic_bytes": frame_alg,
                                "achieved_gbs": frame_alg / ((ms_total / K) * 1e-3) / 1e9,
