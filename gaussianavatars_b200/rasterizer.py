@@ -137,6 +137,9 @@ def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
         stream = torch.cuda.current_stream(device).cuda_stream
         n = N.lib().gab200_forward(C.byref(a), C.byref(st), C.c_void_p(stream))
     N.check(n, "gab200_forward")
+    if len(_binning_hint) > 256:   # P changes at every densification: do not let the per-shape hints pile up
+        _binning_hint.clear()
+        _depth_hint.clear()
     _binning_hint[(device, a.image_width, a.image_height, P)] = min(int(n * 1.25) + 4096, 2**31 - 1)
     if st.depth_key_min <= st.depth_key_max:
         _depth_hint[(device, a.image_width, a.image_height, P)] = _widen_depth_range(st.depth_key_min, st.depth_key_max)
