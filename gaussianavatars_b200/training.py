@@ -26,8 +26,8 @@ class _PhotometricLoss(torch.autograd.Function):
         device = image.device
         if device.type != "cuda":
             raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
-        if image.dtype != torch.float32 or image.dim() != 3:
-            raise TypeError("image must be a float32 (C, H, W) tensor")
+        if image.dtype != torch.float32 or image.dim() not in (3, 4):
+            raise TypeError("image must be a float32 (C, H, W) or (B, C, H, W) tensor")
         if gt.shape != image.shape or gt.device != device:
             raise ValueError(f"gt must have the image's shape {tuple(image.shape)} on {device}, got {tuple(gt.shape)} on {gt.device}")
         if gt.dtype not in (torch.uint8, torch.float32):
@@ -36,7 +36,8 @@ class _PhotometricLoss(torch.autograd.Function):
             raise ValueError("lambda_dssim must lie in [0, 1]")
         img = image if image.is_contiguous() else image.contiguous()
         g = gt if gt.is_contiguous() else gt.contiguous()
-        Cc, H, W = img.shape
+        H, W = int(img.shape[-2]), int(img.shape[-1])
+        Cc = img.numel() // max(H * W, 1)   # a batch is just more independent planes: the means run over all of them
         grad = torch.empty_like(img)
         scratch = torch.empty(N.PHOTOMETRIC_SCRATCH_HEAD + 3 * img.numel(), dtype=torch.float32, device=device)
         loss = torch.empty(3, dtype=torch.float32, device=device)
@@ -62,7 +63,7 @@ class _PhotometricLoss(torch.autograd.Function):
 
 def photometric_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float = 0.2, return_parts: bool = False):
     """`(1 - lambda_dssim) * l1_loss(image, gt) + lambda_dssim * (1 - ssim(image, gt))` of the reference training
-    loop, differentiable w.r.t. `image` (C, H, W float32).  `gt` is float32 in [0, 1] like `viewpoint_cam.original_image`
+    loop, differentiable w.r.t. `image` (float32, (C, H, W) or (B, C, H, W) like the reference's `ssim`).  `gt` is float32 in [0, 1] like `viewpoint_cam.original_image`
     or the uint8 image it was decoded from (value/255 in-kernel: a quarter of the upload).  With `return_parts` also
     returns the detached tensor [l1 mean, ssim mean, total] (for logging, train.py:159-166)."""
     total, parts = _PhotometricLoss.apply(image, gt, lambda_dssim)

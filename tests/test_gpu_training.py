@@ -187,3 +187,25 @@ def test_adam_rejects_what_it_does_not_implement():
     q.grad = torch.ones(4)
     with pytest.raises(RuntimeError):
         g.Adam([q]).step()
+
+
+def test_photometric_loss_accepts_a_batch_like_the_reference_ssim():
+    """(B, C, H, W): every plane is convolved on its own and the means run over everything, so the batched total is
+    the mean of the per-image totals and each gradient is 1/B of the per-image one (utils/loss_utils.py:36-63)."""
+    g = _g()
+    gen = torch.Generator(device="cuda").manual_seed(21)
+    imgs = torch.rand(2, 3, 40, 70, device="cuda", generator=gen)
+    gts = (torch.rand(2, 3, 40, 70, device="cuda", generator=gen) * 255).to(torch.uint8)
+    x = imgs.clone().requires_grad_(True)
+    total, parts = g.photometric_loss(x, gts, LAMBDA, return_parts=True)
+    total.backward()
+    singles, grads = [], []
+    for b in range(2):
+        xb = imgs[b].clone().requires_grad_(True)
+        tb = g.photometric_loss(xb, gts[b], LAMBDA)
+        tb.backward()
+        singles.append(float(tb.detach()))
+        grads.append(xb.grad)
+    assert abs(float(total.detach()) - 0.5 * (singles[0] + singles[1])) < 1e-6
+    assert x.grad.shape == imgs.shape
+    assert torch.allclose(x.grad, 0.5 * torch.stack(grads), rtol=1e-5, atol=1e-12)
