@@ -200,3 +200,23 @@ def test_depth_hint_widening_stays_a_valid_key_range():
     lo, hi = R._widen_depth_range(key(0.73), key(1.31))
     span = key(1.31) - key(0.73)
     assert key(0.73) - lo == span // 8 and hi - key(1.31) == span // 8
+
+
+def test_c_abi_example_compiles_and_links(tmp_path):
+    """examples/abi_forward_backward.cu is the non-Python caller INTEGRATION.md describes: it must build against
+    include/gab200_rasterizer.h from C++ and link against the shared library (running it needs a GPU)."""
+    import shutil
+    from gaussianavatars_b200 import _native as N
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    N.lib()  # the library must exist (build() ran)
+    libdir = os.path.dirname(N.LIB_PATH)
+    exe = tmp_path / "abi_example"
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-ccbin", "/usr/bin/g++",
+           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "abi_forward_backward.cu"),
+           "-L" + libdir, "-lgaussianavatars_b200", "-Xlinker", "-rpath=" + libdir, "-o", str(exe)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert exe.exists()
