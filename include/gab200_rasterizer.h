@@ -13,8 +13,11 @@
  *   - Every pointer is a DEVICE pointer owned by the caller unless stated otherwise; fp32 unless stated.
  *   - Matrices are the row-major flatten of the (4,4) tensors GaussianAvatars builds
  *     (world_view_transform = W2C^T, full_proj_transform = (P W2C)^T; scene/cameras.py:44-46).
- *   - No hidden global state; thread-safe per stream; no exceptions cross the ABI: functions return
- *     >= 0 on success and a negative gab200_status on failure (gab200_status_string() explains it).
+ *   - Nothing a call leaves behind in the library affects a later result: what persists is a launch counter,
+ *     the opt-in stage timers, and per host thread a 64-byte pinned read-back slot and the cub temp-size cache
+ *     (hints such as binning_hint / depth_hint_* travel through the caller).  Thread-safe per stream; no
+ *     exceptions cross the ABI: functions return >= 0 on success and a negative gab200_status on failure
+ *     (gab200_status_string() explains it).
  *   - Scratch memory is obtained through caller-supplied allocation callbacks, mirroring the reference
  *     module's three resizable byte buffers (geometry / binning / image).  The callbacks
  *     are invoked on the calling host thread, must return device memory aligned to 256 B that stays valid
