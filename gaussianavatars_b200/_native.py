@@ -14,9 +14,13 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgaussianavatars_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 INPUT_ACTIVATED = 0
 INPUT_BOUND_RAW = 1
+SYNC_EXACT, SYNC_LATE, SYNC_NONE = 0, 1, 2
+CTR_NOT_MIN_DEPTH_KEY, CTR_MAX_DEPTH_KEY, CTR_NUM_RENDERED, CTR_NUM_LISTED, CTR_BUCKET_OVERFLOW, CTR_CAPACITY, CTR_SEQ = range(7)
+NUM_COUNTERS = 8
+TUNE_HEAVY_FWD, TUNE_HEAVY_BWD, TUNE_DEPTH_SORT = 0, 1, 2
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -28,6 +32,8 @@ class ForwardArgs(C.Structure):
         ("tanfovx", C.c_float), ("tanfovy", C.c_float), ("scale_modifier", C.c_float),
         ("prefiltered", C.c_int32), ("debug", C.c_int32), ("need_backward", C.c_int32), ("binning_hint", C.c_int32),
         ("exact_binning", C.c_int32), ("depth_hint_lo", C.c_uint32), ("depth_hint_hi", C.c_uint32),
+        ("sync_mode", C.c_int32), ("frame_seq", C.c_uint32), ("counters_host", C.c_void_p),
+        ("overflow_flag", C.c_void_p),
         ("bg", C.c_void_p), ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
         ("means3D", C.c_void_p), ("opacities", C.c_void_p), ("scales", C.c_void_p), ("rotations", C.c_void_p),
         ("cov3D_precomp", C.c_void_p), ("shs", C.c_void_p), ("sh_dc", C.c_void_p), ("sh_rest", C.c_void_p),
@@ -47,7 +53,7 @@ class FrameState(C.Structure):
         ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32), ("depth_bits", C.c_int32),
         ("depth_prefix", C.c_uint32), ("binning_capacity", C.c_int64),
         ("depth_key_min", C.c_uint32), ("depth_key_max", C.c_uint32), ("depth_sort_path", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("attempts", C.c_int32), ("device_counters", C.c_void_p),
     ]
 
 
@@ -88,7 +94,7 @@ EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", 
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
                     "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8",
-                    "gab200_photometric_loss", "gab200_adam_step")
+                    "gab200_photometric_loss", "gab200_adam_step", "gab200_tune", "gab200_counters_ok")
 
 _lib = None
 _lock = threading.Lock()
@@ -130,6 +136,10 @@ def lib():
         L.gab200_export_binning.argtypes = [C.POINTER(ForwardArgs), C.POINTER(FrameState), C.c_void_p, C.c_void_p,
                                             C.c_void_p, C.c_void_p]
         L.gab200_launch_count.restype = C.c_int64
+        L.gab200_tune.restype = C.c_int32
+        L.gab200_tune.argtypes = [C.c_int32, C.c_int32]
+        L.gab200_counters_ok.restype = C.c_int32
+        L.gab200_counters_ok.argtypes = [C.c_void_p, C.c_uint32]
         L.gab200_l1_loss_u8.restype = C.c_int32
         L.gab200_l1_loss_u8.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gab200_photometric_loss.restype = C.c_int32
@@ -185,6 +195,11 @@ def host_times(reset: bool = True):
     n = max(out[5], 1.0)
     keys = ("pre_sync_launch", "wait_N", "binning_alloc", "emit_sort_dispatch", "blend_dispatch")
     return {k: out[i] / n for i, k in enumerate(keys)}
+
+
+def tune(knob: int, value: int = -1) -> int:
+    """Set a tuning knob of the library (include/gab200_rasterizer.h GAB200_TUNE_*); returns the previous value."""
+    return int(check(lib().gab200_tune(int(knob), int(value)), "gab200_tune"))
 
 
 def launch_count() -> int:

@@ -1,6 +1,8 @@
 // api.cu -- the extern "C" boundary declared in include/gab200_rasterizer.h.  Host orchestration only: argument
-// validation, carving of the three caller-allocated byte buffers, stage launches, the single host sync that sizes
-// the binning buffer.  No torch types, no exceptions, no global state beyond a launch counter.
+// validation, carving of the three caller-allocated byte buffers, stage launches, and the policy for learning the
+// instance count N (gab200_sync_mode: a wait in the middle, a wait at the end that normally finds its answer ready,
+// or no wait at all under CUDA-graph capture).  No torch types, no exceptions; process-wide state is limited to
+// atomics (launch counter, profiling timers, tuning knobs).
 #include <atomic>
 #include <chrono>
 #include <cstdio>
@@ -58,7 +60,10 @@ static uint32_t depth_bucket_count(int P) {
   while (nb < 8192 && (int64_t)nb * 64 < P) nb <<= 1;
   return nb;
 }
-static GeomView carve_geom(void* base, int P, bool need_backward) {
+// The layout is a pure function of (P, need_backward): the only size that depends on anything else (cub's temp
+// storage for the stage-A radix sort, `sort_temp`) is carved LAST, so the backward -- which passes 0 for it, on
+// whatever host thread autograd picked -- sees every other array at the forward's offset.
+static GeomView carve_geom(void* base, int P, bool need_backward, size_t sort_temp) {
   GeomView g;
   Carver c(base);
   g.rec = c.take<SplatRec>((size_t)P);
@@ -70,8 +75,6 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
   g.depth_keys[1] = c.take<uint32_t>((size_t)P);
   g.ids[0] = c.take<uint32_t>((size_t)P);
   g.ids[1] = c.take<uint32_t>((size_t)P);
-  g.sortA_temp_bytes = cached_sort_temp_bytes(P > 0 ? P : 1, 32);
-  g.sortA_temp = c.take<char>(g.sortA_temp_bytes);
   g.g2d = need_backward ? c.take<float>((size_t)P * GAB_G2D_STRIDE) : nullptr;
   g.face_scratch = need_backward ? c.take<float>((size_t)P * GAB_FACE_GRAD_STRIDE) : nullptr;
   g.scan_temp_bytes = scan_temp_bytes(P);
@@ -91,6 +94,8 @@ static GeomView carve_geom(void* base, int P, bool need_backward) {
     d.scale = 0.f;
     d.enabled = 0;
   }
+  g.sortA_temp_bytes = sort_temp;
+  g.sortA_temp = c.take<char>(sort_temp);
   g.bytes = c.bytes();
   return g;
 }
@@ -102,7 +107,7 @@ struct BinView {
   size_t sort_temp_bytes;
   size_t bytes;
 };
-static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_backward) {
+static BinView carve_binning(void* base, int64_t N, bool need_backward, size_t sort_temp) {
   BinView b;
   Carver c(base);
   // + 320: the blend kernels fetch id lists with 16-B-granular bulk copies of up to 256+4 ids that may start
@@ -113,8 +118,8 @@ static BinView carve_binning(void* base, int64_t N, int sort_bits, bool need_bac
   b.vals[0] = c.take<uint32_t>(n);
   b.vals[1] = c.take<uint32_t>(n);
   b.strip_mask = need_backward ? c.take<uint8_t>(n) : nullptr;
-  b.sort_temp_bytes = cached_sort_temp_bytes(N > 0 ? N : 1, sort_bits);
-  b.sort_temp = c.take<char>(b.sort_temp_bytes);
+  b.sort_temp_bytes = sort_temp;
+  b.sort_temp = c.take<char>(sort_temp);
   b.bytes = c.bytes();
   return b;
 }
@@ -130,7 +135,7 @@ static ImageView carve_image(void* base, int W, int H, bool need_backward) {
   ImageView v;
   Carver c(base);
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
-  v.ranges = c.take<uint2>((size_t)gx * gy);
+  v.ranges = c.take<uint2>((size_t)gx * gy + 1);  // + 1: the slot the sentinel key of a capacity-padded sort maps to
   v.order = c.take<uint32_t>((size_t)gx * gy);
   v.order_info = c.take<uint32_t>(4);
   v.final_T = need_backward ? c.take<float>((size_t)W * H) : nullptr;
@@ -154,9 +159,10 @@ struct StageTimer {
   }
 };
 static StageTimer g_timer;
+static thread_local bool t_capturing = false;  // the calling thread's stream is being captured: no timing events
 struct StageScope {
   int stage; cudaStream_t stream; cudaEvent_t a{}, b{}; bool on;
-  StageScope(int st, cudaStream_t s) : stage(st), stream(s), on(g_timer.enabled.load() != 0) {
+  StageScope(int st, cudaStream_t s) : stage(st), stream(s), on(g_timer.enabled.load() != 0 && !t_capturing) {
     if (on) {
       std::lock_guard<std::mutex> l(g_timer.mu);
       a = g_timer.get(); b = g_timer.get();
@@ -172,7 +178,9 @@ struct StageScope {
   }
 };
 
-static double g_host_us[6] = {0, 0, 0, 0, 0, 0};
+// host-side profile of gab200_forward (nanoseconds, relaxed atomics: any thread may run a forward)
+static std::atomic<int64_t> g_host_ns[6];
+static inline void host_add(int i, double us) { g_host_ns[i].fetch_add((int64_t)(us * 1e3), std::memory_order_relaxed); }
 static inline double now_us() {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -193,15 +201,25 @@ struct PinnedSlot {
 static thread_local PinnedSlot t_slot;
 
 static int check_arch() {
-  static std::atomic<int> cached{0};  // 0 unknown, 1 ok, -1 bad
-  int c = cached.load();
-  if (c != 0) return c;
+  constexpr int MAX_DEV = 64;
+  static std::atomic<int> cached[MAX_DEV];  // per device: 0 unknown, 1 ok, -1 bad
   int dev = 0, major = 0;
   if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+  const bool slot = dev >= 0 && dev < MAX_DEV;
+  int c = slot ? cached[dev].load(std::memory_order_relaxed) : 0;
+  if (c != 0) return c;
   if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return -1;
   c = (major == 10) ? 1 : -1;
-  cached.store(c);
+  if (slot) cached[dev].store(c, std::memory_order_relaxed);
   return c;
+}
+
+// tuning knobs (gab200_tune)
+static std::atomic<int> g_tune[GAB200_NUM_TUNABLES];
+static const int g_tune_default[GAB200_NUM_TUNABLES] = {32, 1024, 0, 0, 0, 0, 0, 0};
+int tune_get(int knob) {
+  const int v = g_tune[knob].load(std::memory_order_relaxed);
+  return v > 0 ? v - 1 : g_tune_default[knob];  // stored biased by one so that zero-initialised = "default"
 }
 
 static bool validate(const gab200_forward_args* a) {
@@ -278,9 +296,23 @@ int64_t gab200_launch_count(void) { return g_launches.load(); }
 
 void gab200_host_times(double out[6], int32_t reset) {
   for (int i = 0; i < 6; i++) {
-    if (out) out[i] = g_host_us[i];
-    if (reset) g_host_us[i] = 0;
+    const int64_t v = reset ? g_host_ns[i].exchange(0) : g_host_ns[i].load();
+    if (out) out[i] = i == 5 ? (double)v : (double)v * 1e-3;
   }
+}
+
+int32_t gab200_tune(int32_t knob, int32_t value) {
+  if (knob < 0 || knob >= GAB200_NUM_TUNABLES) return GAB200_ERR_INVALID_ARGUMENT;
+  const int prev = tune_get(knob);
+  if (value >= 0) g_tune[knob].store(value + 1, std::memory_order_relaxed);
+  return prev;
+}
+
+int32_t gab200_counters_ok(const uint32_t* c, uint32_t frame_seq) {
+  if (c == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
+  const volatile uint32_t* v = c;
+  if (v[GAB200_CTR_SEQ] != frame_seq) return -1;
+  return (v[GAB200_CTR_BUCKET_OVERFLOW] == 0 && v[GAB200_CTR_NUM_RENDERED] <= v[GAB200_CTR_CAPACITY]) ? 1 : 0;
 }
 
 const char* gab200_status_string(int32_t s) {
@@ -295,187 +327,263 @@ const char* gab200_status_string(int32_t s) {
   }
 }
 
+// ---- forward, in pieces ----------------------------------------------------------------------------------
+namespace {
+struct Frame {
+  const gab200_forward_args* a;
+  gab200_frame_state* st;
+  cudaStream_t stream;
+  GeomView g;
+  ImageView iv;
+  int P, W, H, gx, gy;
+  bool nb, dbg;
+  uint32_t* ctr_host;   // where the counters land on the host
+  cudaEvent_t ctr_event;
+  int selA = 0;                           // which half of the stage-A double buffer holds the depth order
+  const uint32_t* order_count = nullptr;  // device count of listed splats (bucket path), else all P are listed
+};
+
+// preprocess (+ bucket bookkeeping when `bucket`) -> per-splat depth order + emission offsets -> counters published
+// on the device and copied to the host slot, event recorded behind the copy.
+int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capacity) {
+  const gab200_forward_args* a = f.a;
+  GeomView& g = f.g;
+  cudaStream_t stream = f.stream;
+  DepthBuckets& d = g.buckets;
+  d.enabled = 0;
+  if (bucket) {
+    d.lo = a->depth_hint_lo;
+    d.hi = a->depth_hint_hi;
+    d.scale = (float)((double)d.nb / ((double)(d.hi - d.lo) + 1.0));
+    d.enabled = 1;
+  }
+  if (run_preprocess) {
+    GAB_CUDA(cudaMemsetAsync(d.counts, 0, g.bucket_clear_bytes, stream));
+    StageScope sc(GAB200_STAGE_PREPROCESS, stream);
+    launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, f.nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], g.buckets,
+                      stream);
+  }
+  GAB_STAGE_CHECK(f.dbg, stream);
+  {
+    StageScope sc(GAB200_STAGE_SCAN, stream);
+    if (bucket) {
+      // per-splat depth order + emission offsets as a bucket sort over the hinted key range -- see binning.cu
+      launch_depth_bucket_sort(f.P, g.buckets, g.depth_keys[0], g.tiles_touched, g.depth_keys[1], g.ids[1], g.offsets, stream);
+      f.selA = 1;
+      f.order_count = g.buckets.meta + GAB200_CTR_NUM_LISTED;
+    } else {
+      // stage A of the key sort (per splat, by depth) + emission offsets in depth order  -- see binning.cu
+      GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], f.P, 32,
+                        &f.selA, stream));
+      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[f.selA], g.tiles_touched, g.offsets, f.P, stream));
+      f.order_count = nullptr;
+    }
+    launch_publish_counters(g.buckets.meta, bucket ? nullptr : g.offsets, f.P, capacity, a->frame_seq,
+                            a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr, stream);
+  }
+  GAB_STAGE_CHECK(f.dbg, stream);
+  GAB_CUDA(cudaMemcpyAsync(f.ctr_host, g.buckets.meta, sizeof(uint32_t) * GAB200_NUM_COUNTERS, cudaMemcpyDeviceToHost,
+                           stream));
+  if (f.ctr_event) GAB_CUDA(cudaEventRecord(f.ctr_event, stream));
+  return GAB200_OK;
+}
+
+// emit -> per-instance tile sort -> ranges -> tile order -> blend, for a binning buffer of `cap` instances.
+// n_known >= 0: exactly that many instances exist (no padding); n_known < 0: the count is only on the device -- the
+// tile sort runs over the whole capacity, unused slots carry the sentinel key and sort behind every tile.
+int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, size_t sort_temp) {
+  const gab200_forward_args* a = f.a;
+  gab200_frame_state* st = f.st;
+  cudaStream_t stream = f.stream;
+  const int tiles = f.gx * f.gy;
+  BinView bv = carve_binning(bin, cap, f.nb, sort_temp);
+  st->binning_capacity = cap;
+  st->binning_buffer = bin;
+  st->binning_bytes = bv.bytes;
+  const int64_t n_sort = n_known >= 0 ? n_known : cap;
+  GAB_CUDA(cudaMemsetAsync(f.iv.ranges, 0, sizeof(uint2) * ((size_t)tiles + 1), stream));
+  if (bv.strip_mask != nullptr && n_sort > 0) GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)n_sort, stream));
+  int selector = 0;
+  if (n_sort > 0) {
+    if (n_known < 0) GAB_CUDA(cudaMemsetAsync(bv.keys[0], 0xff, sizeof(uint32_t) * (size_t)cap, stream));
+    {
+      StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
+      launch_emit_keys(f.P, f.gx, f.gy, f.g.rec, f.g.aux, f.g.ids[f.selA], f.g.offsets, f.order_count, f.g.buckets.meta,
+                       (uint32_t)cap, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+    }
+    GAB_STAGE_CHECK(f.dbg, stream);
+    {
+      StageScope sc(GAB200_STAGE_SORT, stream);
+      GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], n_sort,
+                        st->sort_bits, &selector, stream));
+    }
+    GAB_STAGE_CHECK(f.dbg, stream);
+    {
+      StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+      launch_tile_ranges(n_sort, (uint32_t)tiles, bv.keys[selector], f.iv.ranges, stream);
+    }
+    GAB_STAGE_CHECK(f.dbg, stream);
+  }
+  st->sorted_selector = selector;
+  {
+    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+    launch_tile_order(tiles, f.iv.ranges, f.iv.order, f.iv.order_info, tune_get(GAB200_TUNE_HEAVY_FWD),
+                      tune_get(GAB200_TUNE_HEAVY_BWD), stream);
+  }
+  {
+    StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
+    launch_blend_forward(f.W, f.H, f.iv.ranges, f.iv.order, f.iv.order_info, bv.vals[selector], f.g.rec, a->bg,
+                         a->out_color, f.iv.final_T, f.iv.n_contrib, bv.strip_mask, stream);
+  }
+  GAB_STAGE_CHECK(f.dbg, stream);
+  return GAB200_OK;
+}
+
+int wait_counters(Frame& f) {
+  for (;;) {
+    const cudaError_t q = cudaEventQuery(f.ctr_event);
+    if (q == cudaSuccess) return GAB200_OK;
+    if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
+  }
+}
+}  // namespace
+
 int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!validate(a) || st == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
   if (check_arch() < 0) return GAB200_ERR_ARCH;
   memset(st, 0, sizeof(*st));
-  const int P = a->P, W = a->image_width, H = a->image_height;
-  const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
-  const bool nb = a->need_backward != 0;
-  const bool dbg = a->debug != 0;
+  Frame f;
+  f.a = a; f.st = st; f.stream = stream;
+  f.P = a->P; f.W = a->image_width; f.H = a->image_height;
+  f.gx = (f.W + GAB_TILE - 1) / GAB_TILE; f.gy = (f.H + GAB_TILE - 1) / GAB_TILE;
+  f.nb = a->need_backward != 0;
+  f.dbg = a->debug != 0;
+  const int P = f.P;
+  const int mode = a->sync_mode;
+  const bool speculative = mode != GAB200_SYNC_EXACT;  // binning + blend are enqueued before N is known
+  if (speculative && P > 0 && a->binning_hint <= 0) return GAB200_ERR_INVALID_ARGUMENT;
+  if (mode == GAB200_SYNC_NONE && a->counters_host == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  GAB_CUDA(cudaStreamIsCapturing(stream, &cap_status));
+  if (cap_status != cudaStreamCaptureStatusNone && mode != GAB200_SYNC_NONE) return GAB200_ERR_INVALID_ARGUMENT;
+  struct CaptureGuard {
+    bool prev;
+    explicit CaptureGuard(bool c) : prev(t_capturing) { t_capturing = c; }
+    ~CaptureGuard() { t_capturing = prev; }
+  } capture_guard(cap_status != cudaStreamCaptureStatusNone);
 
   // ---- geometry + image buffers ----
-  GeomView gsz = carve_geom(nullptr, P, nb);
+  const size_t tempA = cached_sort_temp_bytes(P > 0 ? P : 1, 32);
+  GeomView gsz = carve_geom(nullptr, P, f.nb, tempA);
   void* geom = a->alloc_geom(a->alloc_user, gsz.bytes);
   if (geom == nullptr) return GAB200_ERR_ALLOC;
-  GeomView g = carve_geom(geom, P, nb);
-  ImageView isz = carve_image(nullptr, W, H, nb);
+  f.g = carve_geom(geom, P, f.nb, tempA);
+  ImageView isz = carve_image(nullptr, f.W, f.H, f.nb);
   void* img = a->alloc_image(a->alloc_user, isz.bytes);
   if (img == nullptr) return GAB200_ERR_ALLOC;
-  ImageView iv = carve_image(img, W, H, nb);
-  st->geom_buffer = geom; st->geom_bytes = g.bytes;
-  st->image_buffer = img; st->image_bytes = iv.bytes;
-  st->sort_bits = (int)tile_bits((uint32_t)(gx * gy));  // stage B: tile id only
-  st->depth_bits = 32;                                  // stage A: the full fp32 depth pattern
-  st->depth_prefix = 0;
-  int selA = 0;
+  f.iv = carve_image(img, f.W, f.H, f.nb);
+  st->geom_buffer = geom; st->geom_bytes = f.g.bytes;
+  st->image_buffer = img; st->image_bytes = f.iv.bytes;
+  st->sort_bits = (int)tile_bits((uint32_t)(f.gx * f.gy));  // stage B: tile id only
+  st->depth_bits = 32;                                      // stage A: the full fp32 depth pattern
+  st->device_counters = f.g.buckets.meta;
+  st->attempts = 1;
+  st->depth_key_min = 1; st->depth_key_max = 0;  // "nothing visible" until the counters say otherwise
 
-  int64_t N = 0;
   const double t0 = now_us();
-  double t_sync0 = t0, t_sync1 = t0;
-  void* bin = nullptr;
-  size_t bin_bytes_have = 0;
-  bool ranges_cleared = false;
-  int64_t mask_cleared_for = -1;
-  const uint32_t* order_count = nullptr;  // device count of listed splats (bucket path), else all P are listed
-  bool bucket_path = false;
-  if (P > 0) {
-    {
-      static const bool no_bucket = getenv("GAB200_DEPTH_SORT") != nullptr && strcmp(getenv("GAB200_DEPTH_SORT"), "radix") == 0;
-      DepthBuckets& d = g.buckets;
-      if (a->depth_hint_hi > a->depth_hint_lo && !no_bucket) {
-        d.lo = a->depth_hint_lo;
-        d.hi = a->depth_hint_hi;
-        d.scale = (float)((double)d.nb / ((double)(d.hi - d.lo) + 1.0));
-        d.enabled = 1;
-        bucket_path = true;
-      }
-      GAB_CUDA(cudaMemsetAsync(d.counts, 0, g.bucket_clear_bytes, stream));
-    }
-    {
-      StageScope sc(GAB200_STAGE_PREPROCESS, stream);
-      launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], g.buckets,
-                        stream);
-    }
-    GAB_STAGE_CHECK(dbg, stream);
-    if (!t_slot.ok()) return GAB200_ERR_CUDA;
-    if (bucket_path) {
-      // per-splat depth order + emission offsets as a bucket sort over the hinted key range -- see binning.cu
-      StageScope sc(GAB200_STAGE_SCAN, stream);
-      launch_depth_bucket_sort(P, g.buckets, g.depth_keys[0], g.tiles_touched, g.depth_keys[1], g.ids[1], g.offsets, stream);
-      selA = 1;
-      order_count = g.buckets.meta + 3;
-    } else {
-      // stage A of the key sort (per splat, by depth) + emission offsets in depth order  -- see binning.cu
-      StageScope sc(GAB200_STAGE_SCAN, stream);
-      GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], P, 32,
-                        &selA, stream));
-      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[selA], g.tiles_touched, g.offsets, P, stream));
-    }
-    GAB_STAGE_CHECK(dbg, stream);
-    // read back: host[0..7] = meta (min/max key; N, M, overflow on the bucket path), host[8] = N of the radix path
-    GAB_CUDA(cudaMemcpyAsync(t_slot.host, g.buckets.meta, sizeof(uint32_t) * GAB_DEPTH_META_WORDS,
-                             cudaMemcpyDeviceToHost, stream));
-    if (!bucket_path)
-      GAB_CUDA(cudaMemcpyAsync(t_slot.host + 8, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
-    // speculative binning allocation while the GPU is still busy with preprocess + scan
-    t_sync0 = now_us();
-    // ... and everything else that does not need N: the two clears are queued behind the scan right away
-    GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
-    ranges_cleared = true;
-    if (a->binning_hint > 0) {
-      const BinView hv = carve_binning(nullptr, a->binning_hint, st->sort_bits, nb);
-      bin_bytes_have = hv.bytes;
-      bin = a->alloc_binning(a->alloc_user, bin_bytes_have);
-      if (bin == nullptr) return GAB200_ERR_ALLOC;
-      if (nb) {  // strip masks of up to binning_hint instances (same carve as below when N <= hint)
-        const BinView hb = carve_binning(bin, a->binning_hint, st->sort_bits, nb);
-        GAB_CUDA(cudaMemsetAsync(hb.strip_mask, 0, (size_t)a->binning_hint, stream));
-        mask_cleared_for = a->binning_hint;
-      }
-    }
-    const double t_alloc = now_us();
-    g_host_us[2] += t_alloc - t_sync0;
-    t_sync0 = t_alloc;
-    for (;;) {
-      const cudaError_t q = cudaEventQuery(t_slot.ev);
-      if (q == cudaSuccess) break;
-      if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
-    }
-    st->depth_key_min = ~t_slot.host[0];
-    st->depth_key_max = t_slot.host[1];
-    st->depth_sort_path = bucket_path ? 1 : 0;
-    N = (int64_t)(bucket_path ? t_slot.host[2] : t_slot.host[8]);
-    if (bucket_path && t_slot.host[4] != 0) {
-      // a bucket overflowed its shared-memory budget (the hint did not fit this frame): redo on the radix path
-      st->depth_sort_path = 2;
-      GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], P, 32,
-                        &selA, stream));
-      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[selA], g.tiles_touched, g.offsets, P, stream));
-      GAB_CUDA(cudaMemcpyAsync(t_slot.host + 8, g.offsets + (P - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-      GAB_CUDA(cudaEventRecord(t_slot.ev, stream));
-      for (;;) {
-        const cudaError_t q = cudaEventQuery(t_slot.ev);
-        if (q == cudaSuccess) break;
-        if (q != cudaErrorNotReady) return GAB200_ERR_CUDA;
-      }
-      N = (int64_t)t_slot.host[8];
-      order_count = nullptr;
-    }
-    t_sync1 = now_us();
-  }
-  st->num_rendered = N;
-  st->num_candidates = N;
-
-  // keep the speculative carve (sized for the hint) when it is large enough: the layout depends on the capacity
-  int64_t cap = N;
-  if (bin != nullptr && a->binning_hint >= N) {
-    cap = a->binning_hint;
-  } else {
-    BinView bsz = carve_binning(nullptr, N, st->sort_bits, nb);
-    bin = a->alloc_binning(a->alloc_user, bsz.bytes);
+  if (P == 0) {  // nothing to bin: background image, empty ranges
+    BinView bsz = carve_binning(nullptr, 0, f.nb, 0);
+    void* bin = a->alloc_binning(a->alloc_user, bsz.bytes);
     if (bin == nullptr) return GAB200_ERR_ALLOC;
-    mask_cleared_for = -1;
+    GAB_CUDA(cudaMemsetAsync(f.g.buckets.counts, 0, f.g.bucket_clear_bytes, stream));
+    const int rc = enqueue_binning_blend(f, bin, 0, 0, 0);
+    if (rc < 0) return rc;
+    st->num_rendered = st->num_candidates = 0;
+    return 0;
   }
-  const double t_alloc2 = now_us();
-  BinView bv = carve_binning(bin, cap, st->sort_bits, nb);
-  st->binning_capacity = cap;
-  st->binning_buffer = bin; st->binning_bytes = bv.bytes;
 
-  if (!ranges_cleared) GAB_CUDA(cudaMemsetAsync(iv.ranges, 0, sizeof(uint2) * (size_t)gx * gy, stream));
-  if (bv.strip_mask != nullptr && N > 0 && mask_cleared_for < N)
-    GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)N, stream));
-  int selector = 0;
-  if (N > 0) {
-    {
-      StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(P, gx, gy, g.rec, g.aux, g.ids[selA], g.offsets, order_count, bv.keys[0], bv.vals[0],
-                       a->exact_binning, stream);
-    }
-    GAB_STAGE_CHECK(dbg, stream);
-    {
-      StageScope sc(GAB200_STAGE_SORT, stream);
-      GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], N,
-                        st->sort_bits, &selector, stream));
-    }
-    GAB_STAGE_CHECK(dbg, stream);
-    {
-      StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-      launch_tile_ranges(N, bv.keys[selector], iv.ranges, stream);
-    }
-    GAB_STAGE_CHECK(dbg, stream);
+  f.ctr_host = a->counters_host;
+  f.ctr_event = nullptr;
+  if (mode != GAB200_SYNC_NONE) {
+    if (!t_slot.ok()) return GAB200_ERR_CUDA;
+    f.ctr_event = t_slot.ev;
+    if (f.ctr_host == nullptr) f.ctr_host = t_slot.host;
   }
-  st->sorted_selector = selector;
-  {
-    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-    launch_tile_order(gx * gy, iv.ranges, iv.order, iv.order_info, stream);
+  bool bucket = a->depth_hint_hi > a->depth_hint_lo && tune_get(GAB200_TUNE_DEPTH_SORT) == 0;
+  int64_t cap = speculative ? (int64_t)a->binning_hint : 0;
+  int rc = enqueue_geometry(f, bucket, true, (uint32_t)cap);
+  if (rc < 0) return rc;
+
+  // the binning buffer is requested while the GPU is busy with preprocess + depth sort (in every mode)
+  void* bin = nullptr;
+  int64_t bin_cap = 0;
+  size_t tempB = 0;
+  double t_alloc = now_us();
+  host_add(0, t_alloc - t0);
+  if (a->binning_hint > 0) {
+    bin_cap = a->binning_hint;
+    tempB = cached_sort_temp_bytes(bin_cap, st->sort_bits);
+    const BinView hv = carve_binning(nullptr, bin_cap, f.nb, tempB);
+    bin = a->alloc_binning(a->alloc_user, hv.bytes);
+    if (bin == nullptr) return GAB200_ERR_ALLOC;
   }
-  const double t_binned = now_us();
-  {
-    StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
-    launch_blend_forward(W, H, iv.ranges, iv.order, iv.order_info, bv.vals[selector], g.rec, a->bg, a->out_color, iv.final_T, iv.n_contrib,
-                         bv.strip_mask, stream);
+  double t1 = now_us();
+  host_add(2, t1 - t_alloc);
+  if (speculative) {
+    rc = enqueue_binning_blend(f, bin, cap, -1, tempB);
+    if (rc < 0) return rc;
+    const double t2 = now_us();
+    host_add(3, t2 - t1);
+    t1 = t2;
   }
-  GAB_STAGE_CHECK(dbg, stream);
-  const double t_end = now_us();
-  g_host_us[0] += t_sync0 - t0 - 0.0;
-  g_host_us[1] += t_sync1 - t_sync0;
-  g_host_us[2] += t_alloc2 - t_sync1;
-  g_host_us[3] += t_binned - t_alloc2;
-  g_host_us[4] += t_end - t_binned;
-  g_host_us[5] += 1;
+  st->depth_sort_path = bucket ? 1 : 0;
+  if (mode == GAB200_SYNC_NONE) {
+    st->num_rendered = st->num_candidates = -1;
+    g_host_ns[5].fetch_add(1, std::memory_order_relaxed);
+    return 0;
+  }
+
+  // ---- the one host wait: in the middle (EXACT) or at the end, normally already satisfied (LATE) ----
+  rc = wait_counters(f);
+  if (rc < 0) return rc;
+  bool redo = !speculative;
+  if (bucket && f.ctr_host[GAB200_CTR_BUCKET_OVERFLOW] != 0) {
+    // a bucket outgrew its shared-memory budget (the hint did not fit this frame): depth order on the radix path
+    bucket = false;
+    st->depth_sort_path = 2;
+    st->attempts++;
+    rc = enqueue_geometry(f, false, false, (uint32_t)cap);
+    if (rc < 0) return rc;
+    rc = wait_counters(f);
+    if (rc < 0) return rc;
+    redo = true;
+  }
+  const int64_t N = (int64_t)f.ctr_host[GAB200_CTR_NUM_RENDERED];
+  st->depth_key_min = ~f.ctr_host[GAB200_CTR_NOT_MIN_DEPTH_KEY];
+  st->depth_key_max = f.ctr_host[GAB200_CTR_MAX_DEPTH_KEY];
+  st->num_rendered = st->num_candidates = N;
+  double t2 = now_us();
+  host_add(1, t2 - t1);
+  if (speculative && N > cap) {
+    redo = true;
+    st->attempts++;
+  }
+  if (redo) {
+    if (bin == nullptr || N > bin_cap) {  // exact size: the layout depends on the capacity
+      bin_cap = N;
+      tempB = cached_sort_temp_bytes(bin_cap > 0 ? bin_cap : 1, st->sort_bits);
+      const BinView bsz = carve_binning(nullptr, bin_cap, f.nb, tempB);
+      bin = a->alloc_binning(a->alloc_user, bsz.bytes);
+      if (bin == nullptr) return GAB200_ERR_ALLOC;
+    }
+    const double t3 = now_us();
+    host_add(2, t3 - t2);
+    rc = enqueue_binning_blend(f, bin, bin_cap, N, tempB);
+    if (rc < 0) return rc;
+    host_add(3, now_us() - t3);
+  }
+  g_host_ns[5].fetch_add(1, std::memory_order_relaxed);
   return N;
 }
 
@@ -494,9 +602,18 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
   if (bound && a->colors_precomp == nullptr && (b->dL_dsh_dc == nullptr || (a->sh_coeffs > 1 && b->dL_dsh_rest == nullptr)))
     return GAB200_ERR_INVALID_ARGUMENT;
   if (P == 0) return GAB200_OK;
-  GeomView g = carve_geom(st->geom_buffer, P, true);
+  cudaStreamCaptureStatus cap_status = cudaStreamCaptureStatusNone;
+  GAB_CUDA(cudaStreamIsCapturing(stream, &cap_status));
+  struct CaptureGuard {
+    bool prev;
+    explicit CaptureGuard(bool c) : prev(t_capturing) { t_capturing = c; }
+    ~CaptureGuard() { t_capturing = prev; }
+  } capture_guard(cap_status != cudaStreamCaptureStatusNone);
+  GeomView g = carve_geom(st->geom_buffer, P, true, 0);
   ImageView iv = carve_image(st->image_buffer, W, H, true);
-  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, st->sort_bits, true);
+  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, true, 0);
+  if (g.bytes > st->geom_bytes || iv.bytes > st->image_bytes || bv.bytes > st->binning_bytes)
+    return GAB200_ERR_INVALID_ARGUMENT;  // not the buffers this forward carved
 
   GAB_CUDA(cudaMemsetAsync(g.g2d, 0, sizeof(float) * (size_t)P * GAB_G2D_STRIDE, stream));
   if (bound && a->binding != nullptr) {
@@ -511,7 +628,7 @@ int32_t gab200_backward(const gab200_backward_args* b, void* stream_) {
     if (b->dL_dsh_rest && a->sh_coeffs > 1)
       GAB_CUDA(cudaMemsetAsync(b->dL_dsh_rest, 0, sizeof(float) * 3 * (size_t)(a->sh_coeffs - 1) * P, stream));
   }
-  if (st->num_rendered > 0) {
+  if (st->num_rendered != 0) {  // -1: only the device knows (GAB200_SYNC_NONE); empty tile lists cost nothing
     StageScope sc(GAB200_STAGE_BLEND_BWD, stream);
     launch_blend_backward(W, H, iv.ranges, iv.order, iv.order_info, bv.vals[st->sorted_selector], g.rec, a->bg, iv.final_T, iv.n_contrib,
                           b->dL_dout_color, bv.strip_mask, g.g2d, stream);
@@ -614,11 +731,12 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
     return GAB200_ERR_INVALID_ARGUMENT;
   const int W = a->image_width, H = a->image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
-  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, st->sort_bits, a->need_backward != 0);
+  BinView bv = carve_binning(st->binning_buffer, st->binning_capacity, a->need_backward != 0, 0);
   ImageView iv = carve_image(st->image_buffer, W, H, a->need_backward != 0);
+  if (st->num_rendered < 0) return GAB200_ERR_INVALID_ARGUMENT;  // read the counters first (GAB200_SYNC_NONE)
   const size_t N = (size_t)st->num_rendered;
   if (keys && N) {
-    GeomView g = carve_geom(st->geom_buffer, a->P, a->need_backward != 0);
+    GeomView g = carve_geom(st->geom_buffer, a->P, a->need_backward != 0, 0);
     launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], bv.vals[st->sorted_selector], g.aux, keys, stream);
   }
   if (values && N) GAB_CUDA(cudaMemcpyAsync(values, bv.vals[st->sorted_selector], 4 * N, cudaMemcpyDeviceToDevice, stream));

@@ -2,10 +2,13 @@
 // Replaces renderCUDA fwd/bwd of the reference module.
 //
 // B200-first mapping (NOT the reference's 1 thread = 1 pixel, 256-thread block for every tile):
-//   * COLUMN STRIPS: a thread owns K vertically adjacent pixels of one column.  The x-offset to a splat (dx) is
-//     shared by the K pixels, so the exponent costs 3 flops per pixel,
+//   * BANDS: a 16x16 tile is 2 halves (8 columns) x 4 bands (4 rows) = eight 8x4-pixel blocks.  A warp owns one
+//     half and K bands of it; lane = (column 0..7, row-in-band 0..3) and owns the K pixels (column, 4 b + row) of its
+//     bands.  The x-offset to a splat (dx) is shared by a lane's K pixels, so the exponent costs 3 flops per pixel,
 //         power(dy) = p0 + dy * (q + h * dy),   p0 = -A dx^2/2, q = -B dx, h = -C/2   (pre-scaled by log2 e -> ex2),
-//     and the shared-memory broadcast reads of the splat record are amortised K times.
+//     the shared-memory broadcast reads of the splat record are amortised K times, and every instruction of a band
+//     covers a COMPACT 8x4 block: a splat either touches most of its lanes or none (a 16x2 strip, the round-1 shape,
+//     ran its gradient code with 18 of 32 lanes live).
 //   * HYBRID TILE SCHEDULE: the tiles are launched heaviest-first (tile_order_kernel).  A CTA takes either ONE heavy
 //     tile with many warps and few pixels per thread (short per-warp critical path for 2000-deep lists) or SEVERAL
 //     light tiles, each on a 64-thread group with K = 4 (fewest instructions); groups synchronise on their own
@@ -13,15 +16,16 @@
 //     deep tiles, a uniform K = 1 is issue-bound (profiles/r01).
 //   * splat records (48 B, three 16-B quads) are GATHERED straight into shared memory with cp.async (LDGSTS),
 //     double buffered one chunk ahead, ids one further chunk ahead: no register staging, no exposed L2 latency.
-//   * forward records, per sorted instance, which 16x2 pixel strips of its tile it contributed to (one byte);
-//     backward skips every (splat, warp) pair whose strips are all clear before doing any arithmetic.
+//   * forward records, per sorted instance, which of the tile's eight 8x4 blocks it contributed to (one byte);
+//     backward visits a (splat, warp) pair only if one of the warp's blocks is set and then runs code SPECIALISED for
+//     that set of live bands: a warp-uniform switch over the 2^K - 1 live-band sets selects a straight-line body in
+//     which the live bands' dependency chains interleave (ILP) and dead bands cost nothing; lanes whose pixel did
+//     not contribute carry alpha = G = 0 through the same instructions (no divergence, no BSSY/BSYNC, no vote).
 //   * backward: per-lane partial sums over the K pixels collapse to three moments (S0,S1,S2) because dx is
-//     shared; nine per-splat gradient components are then reduced across the warp with a 14-shuffle
-//     multi-value butterfly (instead of 45 shuffles or 9*32 atomics) and leave the SM as ONE 9-lane RED.ADD.F32
-//     per (warp, splat).
+//     shared; eight of the nine per-splat gradient components are transposed through a conflict-free shared-memory
+//     tile (8 STS + 2 LDS.128 + 2 shuffles), the ninth takes 5 shuffles, and they leave the SM as ONE 9-lane
+//     RED.ADD.F32 pair per (warp, splat).
 // Tensor cores are not used: there is no dense contraction on this path (north_star).
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -102,6 +106,22 @@ struct GroupBarrier {
   }
 };
 
+// Pixel ownership inside a 16x16 tile for a group of 256/K threads (thread tl): warp w = tl/32 owns half h = w & 1
+// (columns 8h .. 8h+7) and the K bands (w/2) K .. (w/2) K + K-1 (band b = rows 4b .. 4b+3); lane = (column, row in
+// band).  bit(i) = position of block (h, band i of this warp) in the per-instance block mask byte.
+template <int K>
+struct BandGeom {
+  int col, row0, half, band0;
+  __device__ __forceinline__ explicit BandGeom(int tl) {
+    const int w = tl >> 5, lane = tl & 31;
+    half = w & 1;
+    band0 = (w >> 1) * K;
+    col = half * 8 + (lane & 7);
+    row0 = band0 * 4 + (lane >> 3);
+  }
+  __device__ __forceinline__ int bit(int i) const { return 2 * (band0 + i) + half; }
+};
+
 // =====================================================================================================
 // Forward: one tile on a group of NT = 256/K threads (tl = thread index inside the group)
 // =====================================================================================================
@@ -116,12 +136,13 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   constexpr int NT = 256 / K;
   const int tx = tile % gx, ty = tile / gx;
   const int lane = tl & 31;
-  const int pixx = tx * GAB_TILE + (tl & 15);
-  const int pixy0 = ty * GAB_TILE + (tl >> 4) * K;
+  const BandGeom<K> geo(tl);
+  const int pixx = tx * GAB_TILE + geo.col;
+  const int pixy0 = ty * GAB_TILE + geo.row0;  // the lane's pixel of band i is (pixx, pixy0 + 4 i)
   const float fx = (float)pixx;
   float fy[K];  // pixel rows as floats: dy = py - fy[i] is then independent of K (same bits on every tile schedule)
 #pragma unroll
-  for (int i = 0; i < K; i++) fy[i] = (float)(pixy0 + i);
+  for (int i = 0; i < K; i++) fy[i] = (float)(pixy0 + 4 * i);
   const uint2 range = ranges[tile];
   const int n = (int)(range.y - range.x);
   const uint32_t* ids = point_list + range.x;
@@ -135,7 +156,7 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
 #pragma unroll
   for (int i = 0; i < K; i++) {
     T[i] = 1.f; Cr[i] = Cg[i] = Cb[i] = 0.f; last[i] = 0;
-    if (pixx >= W || pixy0 + i >= H) done |= 1u << i;
+    if (pixx >= W || pixy0 + 4 * i >= H) done |= 1u << i;
   }
 
   const int nchunks = (n + NT - 1) / NT;
@@ -187,13 +208,12 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
     const SplatRec* cur = (c & 1) ? buf1 : buf0;
     const int cnt = min(NT, n - c * NT);
     const uint32_t pos0 = (uint32_t)(c * NT);
-    // Strip bookkeeping for the backward pass, ~2 instructions per splat: every lane records, one bit per splat of
-    // the current 32-splat group, whether its pixels of strip s contributed; at the end of the group one REDUX.OR
-    // per strip turns the lanes' words into "strip s was touched by splat gbase+L" and lane L publishes splat L.
-    constexpr int S = (K + 1) / 2;  // strips a lane's pixels belong to
-    uint32_t lb[S];
+    // Block bookkeeping for the backward pass, ~2 instructions per splat: every lane records, one bit per splat of
+    // the current 32-splat group, whether its pixel of band i contributed; at the end of the group one REDUX.OR per
+    // band turns the lanes' words into "block (half, band i) was touched by splat gbase+L" and lane L publishes splat L.
+    uint32_t lb[K];
 #pragma unroll
-    for (int s_ = 0; s_ < S; s_++) lb[s_] = 0;
+    for (int i = 0; i < K; i++) lb[i] = 0;
     // 32-splat groups: the inner loop is branch-light and unrolled; the per-group epilogue publishes the strip bits
     // and tests saturation once per group
     for (int gbase = 0; gbase < cnt; gbase += 32) {
@@ -221,26 +241,18 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
               Cb[i] = fmaf(r->q2.x, w, Cb[i]);
               T[i] = test_T;
               last[i] = pos0 + (uint32_t)(gbase + jj) + 1u;
-              lb[i >> 1] |= 1u << jj;
+              lb[i] |= 1u << jj;
             }
           }
         }
       }
       if (want_mask) {
         uint32_t wh = 0;
-        const int w_ = tl >> 5;
 #pragma unroll
-        for (int s_ = 0; s_ < S; s_++) {
-          if (K == 1) {
-            const uint32_t rr = __reduce_or_sync(FULLMASK, lb[0]);
-            wh |= ((rr >> lane) & 1u) << w_;
-          } else {
-            const uint32_t rlo = __reduce_or_sync(FULLMASK, lane < 16 ? lb[s_] : 0u);
-            const uint32_t rhi = __reduce_or_sync(FULLMASK, lane < 16 ? 0u : lb[s_]);
-            wh |= ((rlo >> lane) & 1u) << (w_ * K + s_);
-            wh |= ((rhi >> lane) & 1u) << (w_ * K + K / 2 + s_);
-          }
-          lb[s_] = 0;
+        for (int i = 0; i < K; i++) {
+          const uint32_t rr = __reduce_or_sync(FULLMASK, lb[i]);
+          wh |= ((rr >> lane) & 1u) << geo.bit(i);
+          lb[i] = 0;
         }
         if (wh) atomicOr(&smask[gbase + lane], wh);
       }
@@ -258,7 +270,7 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   const size_t HW = (size_t)H * W;
 #pragma unroll
   for (int i = 0; i < K; i++) {
-    const int y = pixy0 + i;
+    const int y = pixy0 + 4 * i;
     if (pixx < W && y < H) {
       const size_t pix = (size_t)y * W + pixx;
       out_color[pix] = fmaf(T[i], bg0, Cr[i]);
@@ -309,76 +321,138 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
   }
 }
 
-static int env_int(const char* name, int dflt) {
-  const char* s = getenv(name);
-  return s ? atoi(s) : dflt;
-}
-
 void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
                           const uint32_t* point_list, const SplatRec* rec, const float* bg, float* out_color,
                           float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, cudaStream_t stream) {
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
-  static const int KH = env_int("GAB200_FWD_KH", 1);
-  static bool configured = false;
-  if (!configured) {
-    const int carve = env_int("GAB200_FWD_CARVEOUT", -1);
-    if (carve >= 0) {
-      cudaFuncSetAttribute(blend_forward_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      cudaFuncSetAttribute(blend_forward_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
-    configured = true;
-  }
   // upper bound on CTAs: every tile heavy; surplus CTAs exit at once
   const int grid = tiles;
-  if (KH == 2)
-    blend_forward_kernel<2><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
-                                                      out_color, final_T, n_contrib, strip_mask);
-  else
-    blend_forward_kernel<1><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
-                                                      out_color, final_T, n_contrib, strip_mask);
+  blend_forward_kernel<1><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
+                                                    out_color, final_T, n_contrib, strip_mask);
   count_launch();
 }
 
 // =====================================================================================================
 // Backward
 // =====================================================================================================
-// Multi-value butterfly: reduces v[0..7] across the 32 lanes with 4+2+1+1+1 = 9 shuffles.  On return every lane
-// holds the warp total of component (lane >> 2).
-__device__ __forceinline__ float warp_reduce8(const float v[8], int lane) {
-  float w[4], u[2];
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const float send = h16 ? v[i] : v[i + 4];
-    const float keep = h16 ? v[i + 4] : v[i];
-    w[i] = keep + __shfl_xor_sync(FULLMASK, send, 16);
-  }
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const float send = h8 ? w[i] : w[i + 2];
-    const float keep = h8 ? w[i + 2] : w[i];
-    u[i] = keep + __shfl_xor_sync(FULLMASK, send, 8);
-  }
-  const float send = h4 ? u[0] : u[1];
-  const float keep = h4 ? u[1] : u[0];
-  float r = keep + __shfl_xor_sync(FULLMASK, send, 4);
-  r += __shfl_xor_sync(FULLMASK, r, 2);
-  r += __shfl_xor_sync(FULLMASK, r, 1);
-  return r;
-}
 __device__ __forceinline__ float warp_reduce1(float v) {
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(FULLMASK, v, m);
   return v;
 }
 
+// Warp sum of eight values per lane through shared memory.  Lanes store v[c] to row c (stride 36 floats: the 32
+// stores of a row and the quarter-warp phases of the 128-bit loads below are both bank-conflict free), then lane L
+// sums the eight values lanes 8 (L & 3) .. 8 (L & 3) + 7 left in row L >> 2 and two shuffles combine the four
+// partial sums: on return every lane holds the warp total of component (lane >> 2).
+#define RED_ROW 36
+#define RED_WORDS (8 * RED_ROW)
+__device__ __forceinline__ float warp_reduce8_smem(const float v[8], float* scratch, int lane) {
+#pragma unroll
+  for (int c = 0; c < 8; c++) scratch[c * RED_ROW + lane] = v[c];
+  __syncwarp();
+  const float4* src = reinterpret_cast<const float4*>(scratch + (lane >> 2) * RED_ROW + (lane & 3) * 8);
+  const float4 a = src[0], b = src[1];
+  float r = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+  r += __shfl_xor_sync(FULLMASK, r, 1);
+  r += __shfl_xor_sync(FULLMASK, r, 2);
+  return r;
+}
+
+// Per-pixel state of the reverse walk (K pixels per lane, one per band).
+template <int K>
+struct PixState {
+  float fy[K];                // pixel row as float
+  float T[K];                 // transmittance in front of the splat being visited (starts at final_T)
+  float ar[K], ag[K], ab[K];  // colour composited behind the splat being visited
+  float dr[K], dg[K], db[K];  // dL/dpixel
+  float bgT[K];               // final_T * (bg . dL/dpixel)
+  int nc[K];                  // n_contrib: only list positions below it contributed to the pixel
+};
+struct SplatSums {  // per-lane sums over the lane's pixels for one splat
+  float S0, S1, S2, go, gr, gg, gb;
+};
+
+// One (splat, warp) visit restricted to the live bands M (compile-time set): straight-line code, the bands'
+// dependency chains are independent and interleave.  A lane whose pixel did not receive this splat in the forward
+// (beyond its n_contrib, outside the footprint, alpha < 1/255) runs the same instructions with alpha = G = 0 and
+// T multiplied by exactly 1: every one of its contributions is an exact zero.
+template <int K, int M>
+__device__ __forceinline__ void visit_bands(PixState<K>& p, int pos, float py, float tA, float dx, float Bp, float Cp,
+                                            float op, float cr, float cg, float cb, SplatSums& s) {
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    if (!((M >> i) & 1)) continue;
+    const float dy = py - p.fy[i];
+    const float pw = fmaf(Cp * dy, dy, fmaf(Bp, dy, tA) * dx);  // the forward's expression, bit for bit
+    const float G = ex2_approx(pw);
+    const float alpha = fminf(0.99f, op * G);
+    const bool valid = pos < p.nc[i] && pw <= 0.f && alpha >= ALPHA_MIN;
+    const float al = valid ? alpha : 0.f;
+    const float Gv = valid ? G : 0.f;
+    const float ra = valid ? rcp_approx(1.f - alpha) : 1.f;
+    const float Tn = p.T[i] * ra;  // transmittance in FRONT of this splat
+    p.T[i] = Tn;
+    const float w = al * Tn;
+    s.gr = fmaf(w, p.dr[i], s.gr);
+    s.gg = fmaf(w, p.dg[i], s.gg);
+    s.gb = fmaf(w, p.db[i], s.gb);
+    // dL/dalpha = T * sum_ch (c - colour behind) dpix  -  T_final/(1-alpha) * (bg . dpix)
+    const float er = cr - p.ar[i], eg = cg - p.ag[i], eb = cb - p.ab[i];
+    float dLda = er * p.dr[i];
+    dLda = fmaf(eg, p.dg[i], dLda);
+    dLda = fmaf(eb, p.db[i], dLda);
+    dLda = fmaf(dLda, Tn, -p.bgT[i] * ra);
+    // colour behind the NEXT (nearer) splat: this one composited over what was behind it
+    p.ar[i] = fmaf(al, er, p.ar[i]);
+    p.ag[i] = fmaf(al, eg, p.ag[i]);
+    p.ab[i] = fmaf(al, eb, p.ab[i]);
+    const float t = Gv * dLda;  // G dL/dalpha
+    s.go += t;
+    const float s_ = op * t;    // G dL/dG
+    const float sd = s_ * dy;
+    s.S0 += s_;
+    s.S1 += sd;
+    s.S2 = fmaf(sd, dy, s.S2);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ void visit_switch(uint32_t m, PixState<K>& p, int pos, float py, float tA, float dx,
+                                             float Bp, float Cp, float op, float cr, float cg, float cb,
+                                             SplatSums& s);
+#define GAB_VISIT(M) \
+  case M: visit_bands<K, M>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s); break;
+template <>
+__device__ __forceinline__ void visit_switch<2>(uint32_t m, PixState<2>& p, int pos, float py, float tA, float dx,
+                                                float Bp, float Cp, float op, float cr, float cg, float cb,
+                                                SplatSums& s) {
+  constexpr int K = 2;
+  switch (m) {
+    GAB_VISIT(1) GAB_VISIT(2) GAB_VISIT(3)
+    default: break;
+  }
+}
+template <>
+__device__ __forceinline__ void visit_switch<4>(uint32_t m, PixState<4>& p, int pos, float py, float tA, float dx,
+                                                float Bp, float Cp, float op, float cr, float cg, float cb,
+                                                SplatSums& s) {
+  constexpr int K = 4;
+  switch (m) {
+    GAB_VISIT(1) GAB_VISIT(2) GAB_VISIT(3) GAB_VISIT(4) GAB_VISIT(5) GAB_VISIT(6) GAB_VISIT(7) GAB_VISIT(8)
+    GAB_VISIT(9) GAB_VISIT(10) GAB_VISIT(11) GAB_VISIT(12) GAB_VISIT(13) GAB_VISIT(14) GAB_VISIT(15)
+    default: break;
+  }
+}
+#undef GAB_VISIT
+
 template <int K>
 __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
                                               SplatRec* buf1, uint32_t* bid0, uint32_t* bid1, uint32_t* bm0,
                                               uint32_t* bm1, int* s_max, uint32_t* ids_ring, uint8_t* mask_ring,
-                                              uint64_t* mbar, int W, int H, int gx,
+                                              uint64_t* mbar, float* red, int W, int H, int gx,
                                               const uint2* __restrict__ ranges,
                                               const uint32_t* __restrict__ point_list,
                                               const SplatRec* __restrict__ rec, const float* __restrict__ bg,
@@ -389,39 +463,33 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   constexpr int NT = 256 / K;
   const int tx = tile % gx, ty = tile / gx;
   const int lane = tl & 31;
-  const int pixx = tx * GAB_TILE + (tl & 15);
-  const int pixy0 = ty * GAB_TILE + (tl >> 4) * K;
+  const BandGeom<K> geo(tl);
+  const int pixx = tx * GAB_TILE + geo.col;
+  const int pixy0 = ty * GAB_TILE + geo.row0;
   const float fx = (float)pixx;
-  float fy[K];
-#pragma unroll
-  for (int i = 0; i < K; i++) fy[i] = (float)(pixy0 + i);
   const uint2 range = ranges[tile];
-  const uint32_t* ids = point_list + range.x;
-  const uint8_t* masks = strip_mask + range.x;
-  // strips (rows 2s, 2s+1 of the tile) owned by this warp: 2K rows = K strips starting at warp*K
-  const uint32_t my_strips = ((1u << K) - 1u) << ((tl >> 5) * K);
   const size_t HW = (size_t)H * W;
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
 
-  float T[K], ar[K], ag[K], ab[K], dr[K], dg[K], db[K], bgT[K];
-  int nc[K];
+  PixState<K> p;
   int my_max = 0;
 #pragma unroll
   for (int i = 0; i < K; i++) {
-    const int y = pixy0 + i;
-    ar[i] = ag[i] = ab[i] = 0.f;
+    const int y = pixy0 + 4 * i;
+    p.fy[i] = (float)y;
+    p.ar[i] = p.ag[i] = p.ab[i] = 0.f;
     if (pixx < W && y < H) {
       const size_t pix = (size_t)y * W + pixx;
-      T[i] = final_T[pix];
-      nc[i] = (int)n_contrib[pix];
-      dr[i] = dL_dpix[pix];
-      dg[i] = dL_dpix[HW + pix];
-      db[i] = dL_dpix[2 * HW + pix];
+      p.T[i] = final_T[pix];
+      p.nc[i] = (int)n_contrib[pix];
+      p.dr[i] = dL_dpix[pix];
+      p.dg[i] = dL_dpix[HW + pix];
+      p.db[i] = dL_dpix[2 * HW + pix];
     } else {
-      T[i] = 0.f; nc[i] = 0; dr[i] = dg[i] = db[i] = 0.f;
+      p.T[i] = 0.f; p.nc[i] = 0; p.dr[i] = p.dg[i] = p.db[i] = 0.f;
     }
-    bgT[i] = T[i] * (bg0 * dr[i] + bg1 * dg[i] + bg2 * db[i]);
-    my_max = max(my_max, nc[i]);
+    p.bgT[i] = p.T[i] * (bg0 * p.dr[i] + bg1 * p.dg[i] + bg2 * p.db[i]);
+    my_max = max(my_max, p.nc[i]);
   }
   // the tile only needs instances [0, max n_contrib): nothing behind the last contributor of any pixel matters
   if (tl == 0) *s_max = 0;
@@ -435,7 +503,7 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;
 
   // reverse walk: chunk c covers positions n-1-c*NT-j (j = 0..NT-1), i.e. the ascending run [lo_c, lo_c + NT) with
-  // lo_c = max(0, n - (c+1) NT).  Ids and strip masks of a chunk arrive by two TMA bulk copies on one mbarrier
+  // lo_c = max(0, n - (c+1) NT).  Ids and block masks of a chunk arrive by two TMA bulk copies on one mbarrier
   // (same 16-B alignment treatment as in the forward), two chunks ahead.
   constexpr int ID_STRIDE = NT + 4;    // u32 per ring slot
   constexpr int MK_STRIDE = NT + 16;   // bytes per ring slot
@@ -457,13 +525,13 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   auto wait_lists = [&](int k) { mbar_wait(&mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1)); };
   // this thread's (id, mask) of chunk k: reverse index p = k NT + tl  <->  position n-1-p
   auto my_entry = [&](int k, uint32_t& id, uint32_t& mask) {
-    const int p = k * NT + tl;
+    const int q = k * NT + tl;
     id = 0xffffffffu;
     mask = 0u;
-    if (p < n) {
+    if (q < n) {
       const int lo = chunk_lo(k);
       const uint32_t g0 = range.x + (uint32_t)lo;
-      const int rel = (n - 1 - p) - lo;
+      const int rel = (n - 1 - q) - lo;
       id = ids_ring[(k % ID_RING) * ID_STRIDE + (int)(g0 & 3u) + rel];
       mask = mask_ring[(k % ID_RING) * MK_STRIDE + (int)(g0 & 15u) + rel];
     }
@@ -479,6 +547,17 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   bid0[tl] = id_cur;
   bm0[tl] = mask_cur;
   cp_async_commit();
+
+  // this warp's K blocks inside the mask byte: bits geo.bit(0), geo.bit(0) + 2, ... (one half, consecutive bands)
+  const int bit0 = geo.bit(0);
+  auto my_bands = [&](uint32_t mask) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++) m |= ((mask >> (bit0 + 2 * i)) & 1u) << i;
+    return m;
+  };
+  float* red_w = red + (tl >> 5) * (2 * RED_WORDS);
+  uint32_t flip = 0;
 
   for (int c = 0; c < nchunks; c++) {
     const bool odd = (c & 1) != 0;
@@ -498,66 +577,45 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
     const uint32_t* cur_id = odd ? bid1 : bid0;
     const uint32_t* cur_mask = odd ? bm1 : bm0;
     const int cnt = min(NT, n - c * NT);
-    for (int j = 0; j < cnt; j++) {
-      // the forward recorded which pixel strips this splat contributed to: no strip of this warp -> nothing to do
-      if ((cur_mask[j] & my_strips) == 0) continue;
-      const int pos = n - 1 - c * NT - j;  // 0-based position in the tile's list; contributes to pixel iff pos < nc
-      const float4 q0 = cur[j].q0;
-      const float4 q1 = cur[j].q1;
-      const float cbl = cur[j].q2.x;
-      const float dx = q0.x - fx;
-      const float tA = q0.z * dx;  // conic is stored pre-scaled: (A',B',C') = (-A/2, -B, -C/2) * log2(e)
-      const float A = q0.z * CONIC_UNSCALE_AC, B = q0.w * CONIC_UNSCALE_B, C = q1.x * CONIC_UNSCALE_AC, op = q1.y;
-      float S0 = 0.f, S1 = 0.f, S2 = 0.f, go = 0.f, gr = 0.f, gg = 0.f, gb = 0.f;
-      bool any = false;
-#pragma unroll
-      for (int i = 0; i < K; i++) {
-        const float dy = q0.y - fy[i];
-        const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
-        const float G = ex2_approx(pw);
-        const float alpha = fminf(0.99f, op * G);
-        if (pos < nc[i] && pw <= 0.f && alpha >= ALPHA_MIN) {
-          any = true;
-          const float ra = rcp_approx(1.f - alpha);
-          T[i] *= ra;  // transmittance in FRONT of this splat
-          const float w = alpha * T[i];
-          gr = fmaf(w, dr[i], gr);
-          gg = fmaf(w, dg[i], gg);
-          gb = fmaf(w, db[i], gb);
-          // dL/dalpha = T * sum_ch (c - colour behind) dpix  -  T_final/(1-alpha) * (bg . dpix)
-          float dLda = (q1.z - ar[i]) * dr[i];
-          dLda = fmaf(q1.w - ag[i], dg[i], dLda);
-          dLda = fmaf(cbl - ab[i], db[i], dLda);
-          dLda = fmaf(dLda, T[i], -bgT[i] * ra);
-          // colour behind the NEXT (nearer) splat: this one composited over what was behind it
-          ar[i] = fmaf(alpha, q1.z - ar[i], ar[i]);
-          ag[i] = fmaf(alpha, q1.w - ag[i], ag[i]);
-          ab[i] = fmaf(alpha, cbl - ab[i], ab[i]);
-          go = fmaf(G, dLda, go);
-          const float s_ = G * op * dLda;  // G * dL/dG
-          const float sd = s_ * dy;
-          S0 += s_;
-          S1 += sd;
-          S2 = fmaf(sd, dy, S2);
-        }
+    for (int gbase = 0; gbase < cnt; gbase += 32) {
+      // lane L looks at entry gbase + L: which of this warp's bands did it touch?  The warp then walks the entries
+      // with a non-empty set in order (ascending j = back to front).
+      const uint32_t mine = (gbase + lane < cnt) ? my_bands(cur_mask[gbase + lane]) : 0u;
+      uint32_t todo = __ballot_sync(FULLMASK, mine != 0u);
+      while (todo) {
+        const int jj = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const uint32_t m = __shfl_sync(FULLMASK, mine, jj);
+        const int j = gbase + jj;
+        const int pos = n - 1 - c * NT - j;  // 0-based position in the tile's list; contributes to a pixel iff pos < nc
+        const float4 q0 = cur[j].q0;
+        const float4 q1 = cur[j].q1;
+        const float cbl = cur[j].q2.x;
+        const float dx = q0.x - fx;
+        const float tA = q0.z * dx;  // conic is stored pre-scaled: (A',B',C') = (-A/2, -B, -C/2) * log2(e)
+        SplatSums s;
+        s.S0 = s.S1 = s.S2 = s.go = s.gr = s.gg = s.gb = 0.f;
+        visit_switch<K>(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
+        const float A = q0.z * CONIC_UNSCALE_AC, B = q0.w * CONIC_UNSCALE_B, C = q1.x * CONIC_UNSCALE_AC;
+        float v[8];
+        const float dxS0 = dx * s.S0;
+        v[0] = (-A * dxS0 - B * s.S1) * half_W;  // dL/dmean2D.x (NDC units)
+        v[1] = (-C * s.S1 - B * dxS0) * half_H;  // dL/dmean2D.y
+        v[2] = -0.5f * dx * dxS0;                // dL/dconic.xx
+        v[3] = -0.5f * dx * s.S1;                // dL/dconic.xy (stored once)
+        v[4] = -0.5f * s.S2;                     // dL/dconic.yy
+        v[5] = s.go;                             // dL/dopacity
+        v[6] = s.gr;
+        v[7] = s.gg;
+        const float r8 = warp_reduce8_smem(v, red_w + flip, lane);
+        flip ^= RED_WORDS;  // the next visit stores into the other tile: its __syncwarp orders this one's loads
+        const float r1 = warp_reduce1(s.gb);
+        const uint32_t id = cur_id[j];
+        if ((lane & 3) == 0)
+          atomicAdd(g2d + (size_t)id * GAB_G2D_STRIDE + (lane >> 2), r8);
+        else if (lane == 1)
+          atomicAdd(g2d + (size_t)id * GAB_G2D_STRIDE + 8, r1);
       }
-      if (!__any_sync(FULLMASK, any)) continue;
-      float v[8];
-      v[0] = (-A * dx * S0 - B * S1) * half_W;  // dL/dmean2D.x (NDC units)
-      v[1] = (-C * S1 - B * dx * S0) * half_H;  // dL/dmean2D.y
-      v[2] = -0.5f * dx * dx * S0;              // dL/dconic.xx
-      v[3] = -0.5f * dx * S1;                   // dL/dconic.xy (stored once)
-      v[4] = -0.5f * S2;                        // dL/dconic.yy
-      v[5] = go;                                // dL/dopacity
-      v[6] = gr;
-      v[7] = gg;
-      const float r8 = warp_reduce8(v, lane);
-      const float r1 = warp_reduce1(gb);
-      const uint32_t id = cur_id[j];
-      if ((lane & 3) == 0)
-        atomicAdd(g2d + (size_t)id * GAB_G2D_STRIDE + (lane >> 2), r8);
-      else if (lane == 1)
-        atomicAdd(g2d + (size_t)id * GAB_G2D_STRIDE + 8, r1);
     }
     bar.sync();
   }
@@ -565,7 +623,7 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
 }
 
 #ifndef BWD_MIN_BLOCKS
-#define BWD_MIN_BLOCKS 1
+#define BWD_MIN_BLOCKS 4
 #endif
 // CTA = 128 threads: CTAs [0, n_heavy) take one heavy tile with K = 2 (four warps); the rest take two light tiles
 // each, one per 64-thread group with K = 4.
@@ -588,18 +646,20 @@ __global__ void __launch_bounds__(128, BWD_MIN_BLOCKS) blend_backward_kernel(int
   __shared__ __align__(16) uint32_t ids_ring[2][ID_RING * (64 + 4)];   // per 64-thread group; a 128-thread tile uses it flat
   __shared__ __align__(16) uint8_t mask_ring[2][ID_RING * (64 + 16)];
   __shared__ __align__(8) uint64_t mbar[2][ID_RING];
+  __shared__ __align__(16) float red[4 * 2 * RED_WORDS];  // per warp: two transposition tiles used alternately
   const int nh = (int)order_info[1];
   const int b = blockIdx.x, t = threadIdx.x;
   if (b < nh) {
     backward_tile<2>((int)order[b], t, GroupBarrier<128>{0}, buf[0], buf[1], bid[0], bid[1], bm[0], bm[1], &s_max[0],
-                     &ids_ring[0][0], &mask_ring[0][0], mbar[0], W, H, gx, ranges, point_list, rec, bg, final_T,
+                     &ids_ring[0][0], &mask_ring[0][0], mbar[0], red, W, H, gx, ranges, point_list, rec, bg, final_T,
                      n_contrib, dL_dpix, strip_mask, g2d);
   } else {
     const int g = t >> 6, slot = nh + 2 * (b - nh) + g;
     if (slot >= tiles) return;
     backward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
                      bid[0] + g * 64, bid[1] + g * 64, bm[0] + g * 64, bm[1] + g * 64, &s_max[g], ids_ring[g], mask_ring[g],
-                     mbar[g], W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+                     mbar[g], red + g * (2 * 2 * RED_WORDS), W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
+                     dL_dpix, strip_mask, g2d);
   }
 }
 

@@ -21,6 +21,7 @@ namespace gab {
 #define SH_C3_6 -0.5900435899266435f
 
 void count_launch();
+int tune_get(int knob);  // api.cu: current value of a gab200_tune() knob
 
 // Exact per-tile-row span of the region where a splat can reach alpha >= 1/255:
 //   q(d) = 1/2 (A dx^2 + C dy^2) + B dx dy <= ln(255 * opacity)          (the blend's own accept test)
@@ -71,7 +72,7 @@ struct TileSpan {
 // ---- launchers (each counts its launches) ----
 // Per-splat depth sort as a bucket sort (binning.cu header): bookkeeping arrays in the geometry buffer.
 #define GAB_DEPTH_BUCKET_CAP 2048   // splats one bucket may hold before the frame falls back to the radix path
-#define GAB_DEPTH_META_WORDS 8      // [0] ~min key, [1] max key, [2] N, [3] M (splats with instances), [4] overflow flag
+#define GAB_DEPTH_META_WORDS GAB200_NUM_COUNTERS  // the frame counters of the public header (GAB200_CTR_*)
 struct DepthBuckets {
   uint32_t* counts;     // [nb] splats per bucket           } zeroed together with meta before preprocess
   uint32_t* tiles;      // [nb] instances per bucket        }
@@ -102,13 +103,20 @@ void launch_depth_bucket_sort(int P, const DepthBuckets& buckets, const uint32_t
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
+// counters[NUM_RENDERED / NUM_LISTED] of a radix-sorted frame (offsets != nullptr), capacity and sequence number
+void launch_publish_counters(uint32_t* counters, const uint32_t* offsets, int P, uint32_t capacity, uint32_t seq,
+                             uint32_t* sticky_overflow, cudaStream_t stream);
+// `capacity`: instances the key/value arrays hold -- anything beyond is dropped (the frame's counters say so);
+// counters[BUCKET_OVERFLOW] != 0 (depth order unusable) emits nothing.
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
-                      const uint32_t* offsets, const uint32_t* order_count, uint32_t* keys, uint32_t* vals,
-                      int exact_binning, cudaStream_t stream);
-void launch_tile_ranges(int64_t N, const uint32_t* keys, uint2* ranges, cudaStream_t stream);
+                      const uint32_t* offsets, const uint32_t* order_count, const uint32_t* counters, uint32_t capacity,
+                      uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
+// keys[0..N) sorted; entries with key >= tiles are padding (sentinel) behind the last real instance
+void launch_tile_ranges(int64_t N, uint32_t tiles, const uint32_t* keys, uint2* ranges, cudaStream_t stream);
 void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
                         cudaStream_t stream);
-void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream);
+void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, int heavy_fwd,
+                       int heavy_bwd, cudaStream_t stream);
 
 // binning.cu (cub)
 size_t scan_temp_bytes(int P);

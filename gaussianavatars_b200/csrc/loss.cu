@@ -8,12 +8,14 @@
 
 namespace gab {
 
+// VEC: img/grad 16-B aligned and gt 4-B aligned (checked by the launcher); otherwise every thread takes the scalar loop.
+template <bool VEC>
 __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float* __restrict__ img,
                                                          const uint8_t* __restrict__ gt, float inv_n,
                                                          float* __restrict__ grad, float* __restrict__ loss_sum) {
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   float acc = 0.f;
-  if (i4 + 3 < n) {
+  if (VEC && i4 + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(img + i4);
     const uchar4 g = *reinterpret_cast<const uchar4*>(gt + i4);
     const float d0 = v.x - __fdiv_rn((float)g.x, 255.f), d1 = v.y - __fdiv_rn((float)g.y, 255.f);
@@ -22,7 +24,7 @@ __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float*
     auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
     *reinterpret_cast<float4*>(grad + i4) = make_float4(sgn(d0) * inv_n, sgn(d1) * inv_n, sgn(d2) * inv_n, sgn(d3) * inv_n);
   } else {
-    for (int64_t i = i4; i < n; i++) {
+    for (int64_t i = i4; i < n && i < i4 + 4; i++) {
       const float d = img[i] - __fdiv_rn((float)gt[i], 255.f);
       acc += fabsf(d);
       grad[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
@@ -44,7 +46,12 @@ __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float*
 void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, cudaStream_t stream) {
   if (n == 0) return;
   const int64_t threads = (n + 3) / 4;
-  l1_loss_u8_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, grad, loss);
+  const bool aligned = (((uintptr_t)img | (uintptr_t)grad) & 15) == 0 && ((uintptr_t)gt & 3) == 0;
+  const unsigned blocks = (unsigned)((threads + 255) / 256);
+  if (aligned)
+    l1_loss_u8_kernel<true><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, grad, loss);
+  else  // a contiguous view with a storage offset (batch[b], a uint8 slice): same result through scalar accesses
+    l1_loss_u8_kernel<false><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, grad, loss);
   count_launch();
 }
 

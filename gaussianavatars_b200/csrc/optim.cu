@@ -98,12 +98,13 @@ void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step
   const double bc1 = 1.0 - pow(beta1, (double)step);
   const double bc2 = 1.0 - pow(beta2, (double)step);
   const float inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
-  for (int base = 0; base < num_segments; base += GAB_ADAM_MAX_SEGMENTS) {
+  int next = 0;  // first input segment not yet consumed (empty segments are skipped without filling a slot)
+  while (next < num_segments) {
     AdamBatch b;
     int cnt = 0;
     int64_t longest = 0;
-    for (int i = base; i < num_segments && cnt < GAB_ADAM_MAX_SEGMENTS; i++) {
-      const gab200_adam_segment& s = segs[i];
+    for (; next < num_segments && cnt < GAB_ADAM_MAX_SEGMENTS; next++) {
+      const gab200_adam_segment& s = segs[next];
       if (s.n <= 0) continue;
       b.p[cnt] = s.param;
       b.g[cnt] = s.grad;

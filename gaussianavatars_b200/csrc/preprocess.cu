@@ -7,8 +7,6 @@
 // Replaces, in ONE kernel (SURVEY.md 2.4 K1 + the eager getters of 2.4(b)):
 //   scene/gaussian_model.py:113-160   get_xyz / get_rotation / get_scaling / get_opacity / get_features
 //   diff_gaussian_rasterization preprocessCUDA (absent submodule; behaviour: SURVEY.md Appendix B.1)
-#include <cstdlib>
-
 #include "common.cuh"
 #include "kernels.cuh"
 #include "splat_math.cuh"
@@ -460,9 +458,12 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
                                                         const uint32_t* __restrict__ order,
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ order_count,
+                                                        const uint32_t* __restrict__ counters, uint32_t cap,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                         int exact_binning) {
   constexpr unsigned FULL = 0xffffffffu;
+  // a depth bucket overflowed: `order` / `offsets` are incomplete, the host (or the graph's owner) redoes the frame
+  if (order_count != nullptr && counters[GAB200_CTR_BUCKET_OVERFLOW] != 0) return;
   const int lane = threadIdx.x & 31;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int slot = warp_global * 32 + lane;  // position in DEPTH order; the splat it holds is order[slot]
@@ -499,8 +500,10 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const uint32_t sid = __shfl_sync(FULL, i, src);
       for (int t = lane; t < cnt; t += 32) {
         const int y = sy0 + t / w, x = sx0 + t % w;
-        keys[soff + t] = (uint32_t)(y * gx + x);
-        vals[soff + t] = sid;
+        if (soff + t < cap) {
+          keys[soff + t] = (uint32_t)(y * gx + x);
+          vals[soff + t] = sid;
+        }
       }
     }
     return;
@@ -515,8 +518,10 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       int cx0, cx1;
       span.row(ty, cx0, cx1);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = (uint32_t)(ty * gx + x);
-        vals[o] = i;
+        if (o < cap) {
+          keys[o] = (uint32_t)(ty * gx + x);
+          vals[o] = i;
+        }
         o++;
       }
     }
@@ -546,8 +551,10 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       }
       uint32_t o = base + (uint32_t)(incl - len);
       for (int x = cx0; x < cx1; x++) {
-        keys[o] = (uint32_t)(ty * gx + x);
-        vals[o] = sid;
+        if (o < cap) {
+          keys[o] = (uint32_t)(ty * gx + x);
+          vals[o] = sid;
+        }
         o++;
       }
       base += (uint32_t)__shfl_sync(FULL, incl, 31);
@@ -555,28 +562,50 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   }
 }
 
+__global__ void publish_counters_kernel(uint32_t* __restrict__ counters, const uint32_t* __restrict__ offsets, int P,
+                                        uint32_t capacity, uint32_t seq, uint32_t* __restrict__ sticky_overflow) {
+  if (offsets != nullptr) {  // radix-sorted frame: every splat is listed, N is the last inclusive offset
+    counters[GAB200_CTR_NUM_RENDERED] = offsets[P - 1];
+    counters[GAB200_CTR_NUM_LISTED] = (uint32_t)P;
+    counters[GAB200_CTR_BUCKET_OVERFLOW] = 0;
+  }
+  counters[GAB200_CTR_CAPACITY] = capacity;
+  counters[GAB200_CTR_SEQ] = seq;
+  if (sticky_overflow != nullptr &&
+      (counters[GAB200_CTR_BUCKET_OVERFLOW] != 0 || counters[GAB200_CTR_NUM_RENDERED] > capacity))
+    *sticky_overflow = 1u;
+}
+void launch_publish_counters(uint32_t* counters, const uint32_t* offsets, int P, uint32_t capacity, uint32_t seq,
+                             uint32_t* sticky_overflow, cudaStream_t stream) {
+  publish_counters_kernel<<<1, 1, 0, stream>>>(counters, offsets, P, capacity, seq, sticky_overflow);
+  count_launch();
+}
+
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
-                      const uint32_t* offsets, const uint32_t* order_count, uint32_t* keys, uint32_t* vals,
-                      int exact_binning, cudaStream_t stream) {
+                      const uint32_t* offsets, const uint32_t* order_count, const uint32_t* counters, uint32_t cap,
+                      uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, order_count, keys, vals, exact_binning);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, order_count, counters, cap, keys,
+                                                   vals, exact_binning);
   count_launch();
 }
 
 // =====================================================================================================
 // K5: tile ranges from key transitions in the sorted stream (ranges pre-zeroed by the caller).
 // =====================================================================================================
-__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, const uint32_t* __restrict__ keys,
+// Keys >= tiles are the padding of a capacity-sized sort (sentinel 0xffffffff): they sort behind every real instance
+// and all of them land in the spare slot ranges[tiles], which nobody reads.
+__global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, uint32_t tiles, const uint32_t* __restrict__ keys,
                                                           uint2* __restrict__ ranges) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
-  const uint32_t cur = keys[idx];
+  const uint32_t cur = min(keys[idx], tiles);
   if (idx == 0)
     ranges[cur].x = 0;
   else {
-    const uint32_t prev = keys[idx - 1];
+    const uint32_t prev = min(keys[idx - 1], tiles);
     if (cur != prev) {
       ranges[prev].y = (uint32_t)idx;
       ranges[cur].x = (uint32_t)idx;
@@ -639,10 +668,9 @@ __global__ void __launch_bounds__(32 * ORDER_WARPS) tile_order_kernel(int tiles,
   }
 }
 
-void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, cudaStream_t stream) {
+void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, int heavy_fwd,
+                       int heavy_bwd, cudaStream_t stream) {
   if (tiles == 0) return;
-  static const int heavy_fwd = getenv("GAB200_HEAVY_FWD") ? atoi(getenv("GAB200_HEAVY_FWD")) : 32;
-  static const int heavy_bwd = getenv("GAB200_HEAVY_BWD") ? atoi(getenv("GAB200_HEAVY_BWD")) : 1024;
   tile_order_kernel<<<1, 1024, 0, stream>>>(tiles, ranges, order, order_info, heavy_fwd, heavy_bwd);
   count_launch();
 }
@@ -661,11 +689,11 @@ void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* id
   count_launch();
 }
 
-void launch_tile_ranges(int64_t N, const uint32_t* keys, uint2* ranges, cudaStream_t stream) {
+void launch_tile_ranges(int64_t N, uint32_t tiles, const uint32_t* keys, uint2* ranges, cudaStream_t stream) {
   if (N == 0) return;
   const int threads = 256;
   const int64_t blocks = (N + threads - 1) / threads;
-  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, keys, ranges);
+  tile_ranges_kernel<<<(unsigned)blocks, threads, 0, stream>>>(N, tiles, keys, ranges);
   count_launch();
 }
 

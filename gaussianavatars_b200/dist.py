@@ -89,6 +89,7 @@ class SymmetricGradBuffer:
         import torch.distributed._symmetric_memory as symm_mem
 
         self.enabled = False
+        self.pc = pc
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         group = group if group is not None else dist.group.WORLD
@@ -135,16 +136,41 @@ class SymmetricGradBuffer:
     def mc_ptr(self):
         return self.mc_ptrs[self.cur]
 
+    def matches(self, pc=None) -> bool:
+        """True while the model still has the parameter OBJECTS and sizes this buffer was laid out for (densification
+        and pruning replace the nn.Parameters, scene/gaussian_model.py:334-419: call `rebuild()` after them)."""
+        params = list((pc if pc is not None else self.pc).parameters())
+        return (len(params) == len(self.params) and all(a is b for a, b in zip(params, self.params))
+                and sum(p.numel() for p in params) == self.numel)
+
+    def rebuild(self, group=None):
+        """New symmetric buffers for the model's current parameters (collective: every rank must call it)."""
+        self.__init__(self.pc, group if group is not None else getattr(self, "group", None))
+        if self.enabled:
+            self.pc.symm_grad = self
+        return self
+
     def begin(self):
         """Call before backward.  Switches to the replica that every rank zeroed before the previous step's end()
         barrier, and zeroes the other one (whose sums the optimizer has consumed by now) for the step after."""
         prev = self.cur
         self.cur ^= 1
         self.flats[prev].zero_()
+        self.pc._gab200_mc_used = False  # the backward sets it when its gradients really went through the multicast
 
     def end(self):
+        """Call after backward.  Group barrier; then the parameters' .grad are pointed at the reduced replica -- but
+        only if this step's backward took the multicast path for exactly these parameters.  Otherwise (override_color,
+        a model whose parameters were replaced or resized since the buffer was built) the locally stored gradients are
+        the valid ones: they are summed with one NCCL all-reduce instead, and the zeroed replica is left alone."""
         self.handles[self.cur].barrier(channel=1)
-        # autograd may have CLONED the gradient views while the reduction was still in flight (it only adopts a
-        # tensor it holds the sole reference to): point .grad at the reduced buffer itself
-        for p, v in zip(self.params, self.all_views[self.cur]):
-            p.grad = v
+        if getattr(self.pc, "_gab200_mc_used", False) and self.matches():
+            # autograd may have CLONED the gradient views while the reduction was still in flight (it only adopts a
+            # tensor it holds the sole reference to): point .grad at the reduced buffer itself.  With
+            # zero_grad(set_to_none=False) autograd would accumulate INTO a replica that must read zero at its next
+            # turn: these views are replaced every step, and begin() re-zeroes the replica that is about to rest.
+            for p, v in zip(self.params, self.all_views[self.cur]):
+                p.grad = v
+            return True
+        allreduce_splat_grads(self.pc, group=self.group)
+        return False

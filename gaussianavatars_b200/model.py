@@ -132,8 +132,9 @@ class MeshBoundGaussians:
         if self.binding is None:
             return self._xyz
         b = self.binding.long()
-        xyz = torch.bmm(self.face_orien_mat[b], self._xyz[..., None]).squeeze(-1)
-        return xyz * self.face_scaling[b] + self.face_center[b]
+        # p_world = s_face R_face x_local + c_face per splat (SURVEY.md Appendix C "World transform")
+        rotated = torch.einsum("pij,pj->pi", self.face_orien_mat[b], self._xyz)
+        return torch.addcmul(self.face_center[b], rotated, self.face_scaling[b])
 
     @property
     def get_features(self):

@@ -65,6 +65,59 @@ def _cam(t: torch.Tensor, name: str, device):
     return t if t.is_contiguous() else t.contiguous()
 
 
+class FrameHints:
+    """What one caller (one splat model) has learnt about its frames: per (device, W, H, P), the instance count of the
+    last frame (the capacity the next one runs with: gab200_forward_args.binning_hint) and the depth-key range
+    (depth_hint_*).  Hints never change a result, only how much of the forward is enqueued before the host learns N.
+    `render()` keeps one on the model object (`pc._gab200_hints`); callers of the bare operator surface that cannot
+    pass one (the reference's own render() builds a new GaussianRasterizer per frame) share `_default_hints`."""
+
+    MAX_SHAPES = 64  # P changes at every densification: do not let the per-shape hints pile up
+
+    def __init__(self):
+        self.shapes = {}
+        self.seq = 0
+        self.last = None  # info dict of the last forward that used these hints
+
+    def get(self, key):
+        return self.shapes.get(key, (0, (0, 0)))
+
+    def set_depth(self, key, depth_range):
+        self.shapes[key] = (self.get(key)[0], tuple(depth_range))
+
+    def set_capacity(self, key, capacity: int):
+        self.shapes[key] = (int(capacity), self.get(key)[1])
+
+    def put(self, key, n: int, depth_range):
+        if len(self.shapes) >= self.MAX_SHAPES and key not in self.shapes:
+            self.shapes.clear()
+        self.shapes[key] = (min(int(n * 1.25) + 4096, 2**31 - 1), depth_range)
+
+
+_default_hints = FrameHints()
+_SYNC_POLICY = "late"   # "late": sync-free enqueue + end-of-call check whenever a capacity hint exists; "exact": always mid-frame
+
+
+def set_sync_policy(policy: str):
+    """"late" (default) or "exact" -- see include/gab200_rasterizer.h gab200_sync_mode.  Results are identical."""
+    global _SYNC_POLICY
+    if policy not in ("late", "exact"):
+        raise ValueError("policy must be 'late' or 'exact'")
+    _SYNC_POLICY = policy
+
+
+def hints_of(obj) -> "FrameHints":
+    """The FrameHints attached to a model object (created on first use); `_default_hints` if it cannot carry one."""
+    h = getattr(obj, "_gab200_hints", None)
+    if h is None:
+        h = FrameHints()
+        try:
+            obj._gab200_hints = h
+        except Exception:
+            return _default_hints
+    return h
+
+
 def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P: int, need_backward: bool):
     a.abi_version = N.ABI_VERSION
     a.P = P
@@ -78,8 +131,6 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
     a.debug = int(bool(rs.debug))
     a.need_backward = int(need_backward)
     a.exact_binning = int(_EXACT_BINNING)
-    a.binning_hint = _binning_hint.get((device, a.image_width, a.image_height, P), 0)
-    a.depth_hint_lo, a.depth_hint_hi = _depth_hint.get((device, a.image_width, a.image_height, P), (0, 0))
     cams = (_cam(rs.bg, "bg", device), _cam(rs.viewmatrix, "viewmatrix", device),
             _cam(rs.projmatrix, "projmatrix", device), _cam(rs.campos, "campos", device))
     a.bg, a.viewmatrix, a.projmatrix, a.campos = (t.data_ptr() for t in cams)
@@ -88,8 +139,7 @@ def _fill_common(a: N.ForwardArgs, rs: GaussianRasterizationSettings, device, P:
 
 _KEEP_LAST = False
 _last = None
-_binning_hint = {}  # (device, W, H, P) -> expected instance count (last N * 1.25): see gab200_forward_args.binning_hint
-_depth_hint = {}    # (device, W, H, P) -> (lo, hi) depth-key range of the last frame, widened: gab200_forward_args.depth_hint_*
+_last_info = {}
 
 
 def _widen_depth_range(kmin: int, kmax: int):
@@ -125,7 +175,31 @@ def export_last_binning():
     return keys[:n], vals[:n], ranges, n
 
 
-def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
+def last_frame_info() -> dict:
+    """How the last forward on this process went: instances, capacity, depth-sort path, sync mode, attempts."""
+    return dict(_last_info)
+
+
+class CaptureSlot:
+    """What a forward needs while its stream is being captured into a CUDA graph (GAB200_SYNC_NONE): a fixed
+    capacity, a pinned host copy of the frame counters, and a sticky device flag the library raises when a replay
+    overflows the capacity (graph.py owns one per captured step)."""
+
+    def __init__(self, device, capacity: int, depth_range=(0, 0)):
+        self.capacity = int(capacity)
+        self.depth_range = depth_range
+        self.counters = torch.zeros(N.NUM_COUNTERS, dtype=torch.int32).pin_memory()
+        self.flag = torch.zeros(1, dtype=torch.int32, device=device)   # sticky: set by the library on overflow
+        self.flag_host = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.seq = 1
+        self.info = {}
+
+
+_capture_slot = None
+
+
+def _run_forward(a: N.ForwardArgs, device, need_backward: bool, hints: Optional[FrameHints] = None):
+    global _last, _last_info
     H, W, P = a.image_height, a.image_width, a.P
     color = torch.empty((3, H, W), dtype=torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
@@ -133,18 +207,35 @@ def _run_forward(a: N.ForwardArgs, device, need_backward: bool):
     cb, holder = N.begin_forward(device, need_backward)
     a.alloc_geom = a.alloc_binning = a.alloc_image = cb
     st = N.FrameState()
+    key = (device, W, H, P)
+    slot = _capture_slot
+    if slot is not None:      # graph capture: fixed capacity, no host wait; graph.py reads slot.counters after replays
+        a.sync_mode = N.SYNC_NONE
+        a.binning_hint = slot.capacity
+        a.depth_hint_lo, a.depth_hint_hi = slot.depth_range
+        a.frame_seq = slot.seq
+        a.counters_host = slot.counters.data_ptr()
+        a.overflow_flag = slot.flag.data_ptr()
+    else:
+        hints = hints if hints is not None else _default_hints
+        a.binning_hint, (a.depth_hint_lo, a.depth_hint_hi) = hints.get(key)
+        a.sync_mode = N.SYNC_LATE if (_SYNC_POLICY == "late" and a.binning_hint > 0) else N.SYNC_EXACT
+        hints.seq = (hints.seq + 1) & 0x7FFFFFFF
+        a.frame_seq = hints.seq
     with torch.cuda.device(device):
         stream = torch.cuda.current_stream(device).cuda_stream
         n = N.lib().gab200_forward(C.byref(a), C.byref(st), C.c_void_p(stream))
     N.check(n, "gab200_forward")
-    if len(_binning_hint) > 256:   # P changes at every densification: do not let the per-shape hints pile up
-        _binning_hint.clear()
-        _depth_hint.clear()
-    _binning_hint[(device, a.image_width, a.image_height, P)] = min(int(n * 1.25) + 4096, 2**31 - 1)
-    if st.depth_key_min <= st.depth_key_max:
-        _depth_hint[(device, a.image_width, a.image_height, P)] = _widen_depth_range(st.depth_key_min, st.depth_key_max)
+    info = dict(num_rendered=int(st.num_rendered), capacity=int(st.binning_capacity), sync_mode=int(a.sync_mode),
+                depth_sort_path=int(st.depth_sort_path), attempts=int(st.attempts))
+    if slot is not None:
+        slot.info = info
+    else:
+        hints.put(key, n, _widen_depth_range(st.depth_key_min, st.depth_key_max)
+                  if st.depth_key_min <= st.depth_key_max else (0, 0))
+        hints.last = info
+    _last_info = info
     if _KEEP_LAST:
-        global _last
         # pooled (inference) scratch stays valid until the next no_grad forward on this device
         _last = (a, st, holder, device)
     return color, radii, st, holder
@@ -178,7 +269,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         a.means3D, a.opacities = N.ptr(means3D), N.ptr(opacities)
         a.scales, a.rotations, a.cov3D_precomp = N.ptr(scales), N.ptr(rotations), N.ptr(cov3Ds_precomp)
         a.shs, a.colors_precomp = N.ptr(sh), N.ptr(colors_precomp)
-        color, radii, st, holder = _run_forward(a, device, need_bw)
+        color, radii, st, holder = _run_forward(a, device, need_bw, _hints_for_next_call())
         if need_bw:
             ctx.args, ctx.state, ctx.holder = a, st, holder
             ctx.keep = (cams, means3D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, radii)
@@ -215,16 +306,29 @@ class _RasterizeGaussians(torch.autograd.Function):
                 d_cov if cov3Ds_precomp is not None else None, None)
 
 
+_next_hints = None
+
+
+def _hints_for_next_call():
+    global _next_hints
+    h, _next_hints = _next_hints, None
+    return h
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
-                        raster_settings):
+                        raster_settings, hints: Optional[FrameHints] = None):
+    global _next_hints
+    _next_hints = hints  # autograd.Function.apply takes tensors and plain values; the hints object rides beside it
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations,
                                      cov3Ds_precomp, raster_settings)
 
 
 class GaussianRasterizer(nn.Module):
-    def __init__(self, raster_settings: GaussianRasterizationSettings):
+    def __init__(self, raster_settings: GaussianRasterizationSettings, hints: Optional[FrameHints] = None):
+        """`hints` is an extension over the reference's constructor (optional; see FrameHints)."""
         super().__init__()
         self.raster_settings = raster_settings
+        self.hints = hints
 
     def markVisible(self, positions):
         with torch.no_grad():
@@ -247,23 +351,27 @@ class GaussianRasterizer(nn.Module):
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
         return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations,
-                                   cov3D_precomp, self.raster_settings)
+                                   cov3D_precomp, self.raster_settings, self.hints)
 
 
 # ================================================================================================================
 # Fused surface
 # ================================================================================================================
-_face_csr_cache = {}
+_face_csr_cache = {}   # id(binding tensor the caller passed) -> (that tensor, its _version, F, int32 copy, CSR tuple)
 
 
 def _face_csr(binding: torch.Tensor, num_faces: int, chunk: int = 16):
-    """Face-sorted view of `binding` for the backward's per-face reduction (gab200_backward_args.face_*): the binding
-    only changes at densification (scene/gaussian_model.py:472-474,495-497), so this runs once per change."""
-    key = (binding.data_ptr(), binding._version, binding.shape[0], num_faces)
+    """(int32 contiguous binding, face-sorted view of it for the backward's per-face reduction
+    (gab200_backward_args.face_*)).  The binding only changes at densification
+    (scene/gaussian_model.py:472-474,495-497), so this runs once per change.  Keyed on the caller's OWN tensor (a
+    reference is kept, so its id cannot be recycled) and its in-place version: a temporary `.to(int32)` copy whose
+    address the allocator reuses can never alias another model's entry."""
+    key = id(binding)
     hit = _face_csr_cache.get(key)
-    if hit is not None:
-        return hit
-    b = binding.long()
+    if hit is not None and hit[0] is binding and hit[1] == binding._version and hit[2] == num_faces:
+        return hit[3], hit[4]
+    b32 = binding if binding.dtype == torch.int32 and binding.is_contiguous() else binding.to(torch.int32).contiguous()
+    b = b32.long()
     perm = torch.argsort(b, stable=True).to(torch.int32)
     counts = torch.bincount(b, minlength=num_faces)
     starts = torch.cumsum(counts, 0) - counts
@@ -275,10 +383,10 @@ def _face_csr(binding: torch.Tensor, num_faces: int, chunk: int = 16):
     c_end = torch.minimum(c_start + chunk, starts[face] + counts[face])
     out = (perm.contiguous(), face.to(torch.int32).contiguous(), c_start.to(torch.int32).contiguous(),
            c_end.to(torch.int32).contiguous())
-    if len(_face_csr_cache) > 8:
+    if len(_face_csr_cache) >= 8:
         _face_csr_cache.clear()
-    _face_csr_cache[key] = out
-    return out
+    _face_csr_cache[key] = (binding, binding._version, num_faces, b32, out)
+    return b32, out
 
 
 class _RasterizeBound(torch.autograd.Function):
@@ -305,10 +413,10 @@ class _RasterizeBound(torch.autograd.Function):
             _opacity.data_ptr()
         a.sh_dc, a.sh_rest, a.colors_precomp = N.ptr(f_dc), N.ptr(f_rest), N.ptr(colors_precomp)
         F = 0
+        binding_orig = binding
         if binding is not None:
-            if binding.dtype != torch.int32:
-                binding = binding.to(torch.int32)
-            binding = binding.contiguous()
+            if binding.dtype != torch.int32 or not binding.is_contiguous():
+                binding = _face_csr(binding_orig, face_center.shape[0])[0]  # converted once per binding, not per frame
             face_center = _f32c(face_center, "face_center", device)
             face_orien_mat = _f32c(face_orien_mat, "face_orien_mat", device)
             face_scaling = _f32c(face_scaling, "face_scaling", device)
@@ -316,7 +424,8 @@ class _RasterizeBound(torch.autograd.Function):
             a.binding, a.num_faces = binding.data_ptr(), F
             a.face_center, a.face_orien_mat, a.face_scaling = face_center.data_ptr(), face_orien_mat.data_ptr(), \
                 face_scaling.data_ptr()
-        color, radii, st, holder = _run_forward(a, device, need_bw)
+        color, radii, st, holder = _run_forward(a, device, need_bw,
+                                                hints_of(grad_sink) if grad_sink is not None else None)
         if need_bw:
             ctx.args, ctx.state, ctx.holder = a, st, holder
             ctx.keep = (cams, _xyz, _rotation, _scaling, _opacity, f_dc, f_rest, face_center, face_orien_mat,
@@ -326,7 +435,7 @@ class _RasterizeBound(torch.autograd.Function):
                                                             face_scaling.shape)
             # face-frame gradients are only produced when something upstream of the frame trains (FLAME parameters)
             ctx.want_face = binding is not None and any(ctx.needs_input_grad[7:10])
-            ctx.csr = _face_csr(binding, F) if ctx.want_face else None
+            ctx.csr = _face_csr(binding_orig, F)[1] if ctx.want_face else None
         ctx.mark_non_differentiable(radii)
         return color, radii
 
@@ -384,6 +493,7 @@ class _RasterizeBound(torch.autograd.Function):
         ctx.holder = None
         if ctx.grad_sink is not None:  # dist.py: ONE all-reduce over this buffer instead of six
             ctx.grad_sink.flat_grad = flat
+            ctx.grad_sink._gab200_mc_used = bool(use_mc)  # SymmetricGradBuffer.end() only trusts the replica if set
         return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None, None)
 
 

@@ -17,7 +17,7 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, rasterize_bound
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, hints_of, rasterize_bound
 
 
 def _camera_block(cam, device):
@@ -82,7 +82,7 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     except Exception:
         pass
     rs = _settings(viewpoint_camera, pc, pipe, bg_color, scaling_modifier, device)
-    rasterizer = GaussianRasterizer(raster_settings=rs)
+    rasterizer = GaussianRasterizer(raster_settings=rs, hints=hints_of(pc))
     means3D, means2D, opacity = xyz, screenspace_points, pc.get_opacity
     scales = rotations = cov3D_precomp = None
     if getattr(pipe, "compute_cov3D_python", False):

@@ -14,8 +14,9 @@
  *   - Matrices are the row-major flatten of the (4,4) tensors GaussianAvatars builds
  *     (world_view_transform = W2C^T, full_proj_transform = (P W2C)^T; scene/cameras.py:44-46).
  *   - Nothing a call leaves behind in the library affects a later result: what persists is a launch counter,
- *     the opt-in stage timers, and per host thread a 64-byte pinned read-back slot and the cub temp-size cache
- *     (hints such as binning_hint / depth_hint_* travel through the caller).  Thread-safe per stream; no
+ *     the opt-in stage/host timers (atomics), the tuning knobs of gab200_tune(), and per host thread a 64-byte
+ *     pinned read-back slot (hints such as binning_hint / depth_hint_* travel through the caller; the layout of
+ *     the three scratch buffers is a pure function of the arguments).  Thread-safe per stream; no
  *     exceptions cross the ABI: functions return >= 0 on success and a negative gab200_status on failure
  *     (gab200_status_string() explains it).
  *   - Scratch memory is obtained through caller-supplied allocation callbacks, mirroring the reference
@@ -33,7 +34,7 @@
 extern "C" {
 #endif
 
-#define GAB200_ABI_VERSION 2
+#define GAB200_ABI_VERSION 3
 
 typedef enum gab200_status {
   GAB200_OK = 0,
@@ -56,6 +57,36 @@ typedef enum gab200_input_mode {
   GAB200_INPUT_BOUND_RAW = 1
 } gab200_input_mode;
 
+/* How gab200_forward learns N, the number of (splat,tile) instances of the frame (the reference copies it to the
+ * host in the middle of every forward to size its binning buffer: rasterizer_impl.cu). */
+typedef enum gab200_sync_mode {
+  /* One host wait in the MIDDLE of the forward (after preprocess + per-splat depth sort): the binning buffer is
+   * sized for exactly N.  Needs no hint; this is what the first frame of a model uses. */
+  GAB200_SYNC_EXACT = 0,
+  /* binning_hint (> 0) is a hard CAPACITY: the whole forward is enqueued without waiting, then the host waits for
+   * the frame counters at the END of the call (they were written long before in the common case) and, only if the
+   * frame needed more than the capacity or the depth-bucket hint did not fit, re-enqueues the affected stages with
+   * the exact size.  The result is the same as GAB200_SYNC_EXACT's, bit for bit; the GPU never idles behind the host. */
+  GAB200_SYNC_LATE = 1,
+  /* Never waits (required while the stream is being captured into a CUDA graph).  The frame counters are copied
+   * to `counters_host`; the caller inspects them whenever it likes (gab200_counters_ok()).  A frame that overflowed
+   * its capacity was rendered from a truncated instance list (memory-safe, wrong image): redo it with a larger
+   * binning_hint. */
+  GAB200_SYNC_NONE = 2
+} gab200_sync_mode;
+
+/* Frame counters (device: gab200_frame_state.device_counters; host copy: counters_host), 8 x uint32. */
+enum {
+  GAB200_CTR_NOT_MIN_DEPTH_KEY = 0, /* ~(smallest depth key among the splats that emitted instances) */
+  GAB200_CTR_MAX_DEPTH_KEY = 1,
+  GAB200_CTR_NUM_RENDERED = 2,      /* N the frame needs (may exceed the capacity it was given) */
+  GAB200_CTR_NUM_LISTED = 3,        /* splats with at least one instance */
+  GAB200_CTR_BUCKET_OVERFLOW = 4,   /* != 0: a depth bucket outgrew shared memory (depth_hint_* did not fit this frame) */
+  GAB200_CTR_CAPACITY = 5,          /* capacity the binning stages ran with */
+  GAB200_CTR_SEQ = 6,               /* caller's frame_seq echoed back: tells a finished copy from a stale one */
+  GAB200_NUM_COUNTERS = 8
+};
+
 typedef void* (*gab200_alloc_fn)(void* user, size_t bytes);
 
 /* Everything one frame's forward needs.  Replaces the argument list of
@@ -71,9 +102,10 @@ typedef struct gab200_forward_args {
   int32_t prefiltered;     /* accepted for signature parity; the near-plane cull is always applied */
   int32_t debug;           /* 1: synchronise + check after every stage (reference `debug=` flag) */
   int32_t need_backward;   /* 0: inference -- per-pixel state for backward is not written */
-  int32_t binning_hint;    /* expected number of (splat,tile) instances (0 = unknown), e.g. last frame's N * 1.25: the
-                              binning buffer is then requested BEFORE the host sync that reads N back, taking the
-                              allocation off the critical path; it is requested again only if N exceeds the hint */
+  int32_t binning_hint;    /* expected number of (splat,tile) instances (0 = unknown), e.g. last frame's N * 1.25.
+                              GAB200_SYNC_EXACT: the binning buffer is requested BEFORE the host sync that reads N back
+                              (allocation off the critical path; requested again only if N exceeds the hint).
+                              GAB200_SYNC_LATE / NONE: the capacity the binning stages run with (see gab200_sync_mode) */
   int32_t exact_binning;   /* 1: emit the reference's full 3-sigma bounding-square instance list;
                               0: additionally drop (splat,tile) pairs that provably contribute nothing
                                  (alpha < 1/255 over the whole tile): image/gradients unchanged */
@@ -83,6 +115,14 @@ typedef struct gab200_forward_args {
                               cub::DeviceRadixSort + DeviceScan (8 launches); the result is the same bit for bit, and a
                               hint that turns out wrong only costs the time of the radix path on top. */
   uint32_t depth_hint_hi;
+  int32_t sync_mode;       /* gab200_sync_mode */
+  uint32_t frame_seq;      /* any value; echoed in counters[GAB200_CTR_SEQ] */
+  uint32_t* counters_host; /* HOST pointer (pinned memory), GAB200_NUM_COUNTERS words, or NULL: where the frame counters
+                              are copied.  Required for GAB200_SYNC_NONE; the other modes fall back to a slot the
+                              library keeps per host thread. */
+  uint32_t* overflow_flag; /* DEVICE pointer or NULL: the library ORs 1 into it when the frame needed more than its
+                              capacity or its depth buckets overflowed, and never clears it -- a replayed CUDA graph
+                              (GAB200_SYNC_NONE) cannot lose an overflow between two looks at the counters */
 
   /* camera block */
   const float* bg;         /* [3] */
@@ -136,12 +176,19 @@ typedef struct gab200_frame_state {
   uint32_t depth_key_min;     /* smallest / largest depth key among the splats that emitted instances (min > max: none) */
   uint32_t depth_key_max;
   int32_t depth_sort_path;    /* 0: radix sort (no hint); 1: bucket sort; 2: bucket sort overflowed, radix sort redone */
-  int32_t reserved0;
+  int32_t attempts;           /* 1 + number of times stages were re-enqueued (GAB200_SYNC_LATE only; else 1) */
+  const uint32_t* device_counters; /* GAB200_NUM_COUNTERS words inside the geometry buffer (valid as long as it is) */
 } gab200_frame_state;
 
-/* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  Enqueues on `stream` (cudaStream_t as void*);
- * performs ONE host<->device synchronisation on that stream to size the binning buffer (as the reference does). */
+/* Forward.  Returns num_rendered (>= 0) or a negative gab200_status.  With GAB200_SYNC_NONE the count is not known
+ * when the call returns: it returns 0 and sets state_out->num_rendered = -1.  Enqueues on `stream` (cudaStream_t as
+ * void*).  Host<->device synchronisation: see gab200_sync_mode. */
 int64_t gab200_forward(const gab200_forward_args* args, gab200_frame_state* state_out, void* stream);
+
+/* 1 if a GAB200_SYNC_NONE frame whose counters are in `counters` (HOST copy) was rendered from its complete instance
+ * list, 0 if it overflowed (capacity or depth buckets) and has to be redone, -1 if the copy has not landed yet
+ * (counters[GAB200_CTR_SEQ] != frame_seq). */
+int32_t gab200_counters_ok(const uint32_t* counters, uint32_t frame_seq);
 
 /* Gradients.  Replaces rasterize_gaussians_backward.  All outputs are written in full
  * (zeros where a splat received no gradient); NULL outputs are skipped where noted.
@@ -282,6 +329,16 @@ void gab200_stage_timing_enable(int32_t enable);
  * [4] blend dispatch, [5] number of forwards.  Profiling aid; always on (a few clock reads per call). */
 void gab200_host_times(double out[6], int32_t reset);
 int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[GAB200_NUM_STAGES], int32_t reset);
+
+/* Tuning knobs (process-wide, atomics; every value has a built-in default that suits the headline workload).
+ * gab200_tune(knob, value) sets a knob and returns the previous value; value < 0 only queries. */
+enum {
+  GAB200_TUNE_HEAVY_FWD = 0,   /* forward blend: a tile is "heavy" (1 px/thread, 8 warps) from this list length (default 32) */
+  GAB200_TUNE_HEAVY_BWD = 1,   /* backward blend: a tile is "heavy" (K = 2, 4 warps) from this list length (default 1024) */
+  GAB200_TUNE_DEPTH_SORT = 2,  /* 0 (default): bucket sort when a depth hint is given; 1: always cub radix sort */
+  GAB200_NUM_TUNABLES = 8
+};
+int32_t gab200_tune(int32_t knob, int32_t value);
 
 /* Number of kernels launched by this library on the calling process so far (bench.py's gpu_launches claim). */
 int64_t gab200_launch_count(void);

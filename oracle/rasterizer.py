@@ -44,6 +44,13 @@ def load():
     return _lib
 
 
+def set_threads(n: int) -> int:
+    """OpenMP threads of the C oracle (returns the count in effect)."""
+    lib = load()
+    lib.oracle_set_threads.restype = C.c_int
+    return int(lib.oracle_set_threads(C.c_int(int(n))))
+
+
 def _p(a: Optional[np.ndarray]):
     if a is None:
         return C.c_void_p(0)

@@ -17,9 +17,9 @@ def _stream(scene, dev, hint=None, exact=True):
 
     key = (dev, int(scene["W"]), int(scene["H"]), int(scene["means3D"].shape[0]))
     if hint == "none":
-        R._depth_hint.pop(key, None)
+        R._default_hints.set_depth(key, (0, 0))
     elif hint is not None:
-        R._depth_hint[key] = hint
+        R._default_hints.set_depth(key, hint)
     img, radii, _, _ = _run_cuda(scene, dev, exact=exact)
     keys, vals, ranges, n = R.export_last_binning()
     path = int(R._last[1].depth_sort_path)
@@ -97,7 +97,7 @@ def test_bucket_path_with_nothing_visible_and_with_backward():
     grads = []
     for hint in ("none", None):
         if hint == "none":
-            R._depth_hint.clear()
+            R._default_hints.shapes.clear()
         img, radii, t, m2 = _run_cuda(scene, dev, need_grad=True)
         (img * torch.linspace(0, 1, img.numel(), device=dev).view_as(img)).sum().backward()
         grads.append([t[k].grad.clone() for k in ("means3D", "scales", "rotations", "opacities", "shs")] + [m2.grad.clone()])

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in syms:
         assert hasattr(lib, s), f"{s} is declared in include/gab200_rasterizer.h but not exported"
     assert set(N.EXPORTED_SYMBOLS) <= set(syms)
-    assert lib.gab200_abi_version() == N.ABI_VERSION == 2
+    assert lib.gab200_abi_version() == N.ABI_VERSION == 3
     assert b"invalid argument" in lib.gab200_status_string(-1)
     assert b"sm_100" in lib.gab200_status_string(-4)
     assert lib.gab200_launch_count() == 0
