@@ -135,7 +135,8 @@ def test_face_csr_chunks_cover_every_splat_once():
     F = 37
     binding = torch.randint(0, F, (1000,), generator=g).to(torch.int32)
     binding[:300] = 5  # a hot face (several chunks)
-    perm, c_face, c_start, c_end = R._face_csr(binding, F, chunk=16)
+    b32, (perm, c_face, c_start, c_end) = R._face_csr(binding, F, chunk=16)
+    assert b32 is binding  # already int32 + contiguous: no copy
     assert sorted(perm.tolist()) == list(range(1000))
     covered = torch.zeros(1000, dtype=torch.int32)
     for f, s, e in zip(c_face.tolist(), c_start.tolist(), c_end.tolist()):
@@ -144,7 +145,15 @@ def test_face_csr_chunks_cover_every_splat_once():
         assert (binding[ids] == f).all()
         covered[ids] += 1
     assert (covered == 1).all()
-    assert R._face_csr(binding, F, chunk=16)[0] is perm  # cached per binding version
+    assert R._face_csr(binding, F, chunk=16)[1][0] is perm  # cached per binding tensor + version
+    # an int64 binding (the reference's FlameGaussianModel) is converted ONCE, and another tensor never hits its entry
+    b64 = binding.long()
+    c32, csr64 = R._face_csr(b64, F, chunk=16)
+    assert c32.dtype == torch.int32 and R._face_csr(b64, F, chunk=16)[0] is c32
+    other = torch.flip(b64, dims=(0,))
+    assert not torch.equal(R._face_csr(other, F, chunk=16)[1][0], csr64[0])
+    binding[0] = (int(binding[0]) + 1) % F   # in-place edit bumps the version -> rebuilt
+    assert R._face_csr(binding, F, chunk=16)[1][0] is not perm
 
 
 def test_symmetric_grad_buffer_is_inert_without_a_process_group():
