@@ -148,16 +148,26 @@ class GraphedFrame:
         key = (self.device, self.W, self.H, self.pc._xyz.shape[0])
         n_max, lo, hi = 0, 0xFFFFFFFF, 0
         blocks = self._warm if self._warm else [self.cam_host.clone() if self.host_inputs else self.cam.clone()]
-        for rep in range(2):
-            for blk in blocks:
-                (self.cam_host if self.host_inputs else self.cam).copy_(blk)
-                self._body()
-                info = hints.last or {}
-                n_max = max(n_max, int(info.get("num_rendered", 0)))
-                d = hints.get(key)[1]
-                if d[1] > d[0]:  # union of the (already widened) depth-key ranges: one bucket grid fits every camera
-                    lo, hi = min(lo, d[0]), max(hi, d[1])
+        # eager frames on a side stream (torch's recipe for whole-step capture): nothing autograd creates here may be
+        # tied to the legacy default stream
+        cur = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for rep in range(2):
+                for blk in blocks:
+                    (self.cam_host if self.host_inputs else self.cam).copy_(blk)
+                    self._body()
+                    info = hints.last or {}
+                    n_max = max(n_max, int(info.get("num_rendered", 0)))
+                    d = hints.get(key)[1]
+                    if d[1] > d[0]:  # union of the (already widened) depth-key ranges: one bucket grid fits every camera
+                        lo, hi = min(lo, d[0]), max(hi, d[1])
+        cur.wait_stream(side)
         torch.cuda.synchronize(self.device)
+        # release what the eager frames left on the model / on this object (tensors with autograd history)
+        self.pc.face_center = self.pc.face_orien_mat = self.pc.face_scaling = None
+        self.image = self.radii = self.viewspace_points = self.loss = None
         return n_max, ((lo, hi) if hi > lo else (0, 0))
 
     def capture(self, capacity: Optional[int] = None):

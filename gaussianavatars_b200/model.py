@@ -94,6 +94,10 @@ class MeshBoundGaussians:
         """scene/flame_gaussian_model.py:137-147.  On the GPU the frame is ONE library launch; the quaternion form is
         only materialised if the eager reference route asks for it (the fused route composes matrices)."""
         self.verts = verts
+        # drop the previous frame (and the autograd graph hanging off it) BEFORE building the new one: a graph that is
+        # still alive would hand its AccumulateGrad node for `verts` -- bound to the stream of an earlier step -- to the
+        # new graph, which breaks CUDA-graph capture of the step (graph.py)
+        self.face_center = self.face_orien_mat = self.face_scaling = None
         if verts.is_cuda:
             from .rasterizer import face_frame as face_frame_cuda
 
