@@ -178,10 +178,16 @@ def cpu_frames(params, verts, faces, cams, frames, threads=None):
     from oracle import binding as ob
     from oracle import rasterizer as orc
 
-    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: say explicitly how many threads this arm gets
-    threads = threads or (os.cpu_count() or 1)
-    torch.set_num_threads(threads)
-    orc.set_threads(threads)
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: say explicitly how many threads this arm gets.
+    # The C oracle (its own libgomp) gets every logical CPU; torch's intra-op pool keeps its default (one thread per
+    # physical core) unless the launcher forced it to 1 -- two pools of spinning threads on every logical CPU
+    # oversubscribe the box (measured: the eager binding getters went from 19 ms to 3.5 s per frame).
+    cpus = os.cpu_count() or 1
+    orc.set_threads(threads or cpus)
+    if threads:
+        torch.set_num_threads(threads)
+    elif torch.get_num_threads() == 1 and cpus > 1:
+        torch.set_num_threads(max(1, cpus // 2))
     bg = np.ones(3, np.float32)
     gout = torch.randn(3, HEIGHT, WIDTH, generator=torch.Generator().manual_seed(1)).numpy()
     from gaussianavatars_b200 import synthetic as syn
@@ -399,6 +405,7 @@ def main():
 
     # ---- e2e: host-resident inputs -----------------------------------------------------------------------------------
     gt_host = [torch.randint(0, 256, (3, HEIGHT, WIDTH), dtype=torch.uint8) for _ in range(2)]
+    gt_pin = [t.pin_memory() for t in gt_host]
     cam_host_blocks = [camera_block(c).pin_memory() for c in my_cams]
     h2d_bytes = gt_host[0].numel() + cam_host_blocks[0].numel() * 4
     losses = []
@@ -410,17 +417,21 @@ def main():
             f_ = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="l1_u8", host_inputs=True,
                               warm_cameras=cam_host_blocks,
                               after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
-            f_.set_inputs(camera=cam_host_blocks[0], verts=posed[0].detach(), gt_u8=gt_host[k])
+            f_.set_inputs(camera=cam_host_blocks[0], verts=posed[0].detach(), gt_u8=gt_pin[k])
             f_.capture()
             e2e_frames.append(f_)
         done = [torch.cuda.Event() for _ in range(2)]
+        e2e_frames[0].set_inputs(gt_u8=gt_pin[0])   # the first step's ground truth is on its way before the clock starts
 
         def step_e2e(i):
             f_ = e2e_frames[i % 2]
             f_.cam_host.copy_(cam_host_blocks[i % len(cam_host_blocks)])   # 140-byte host write into pinned staging
             f_.set_inputs(verts=posed[i % len(posed)].detach())
-            f_.run()
+            f_.run()                                                        # waits (on the GPU) for this step's upload
             done[i % 2].record()
+            # the NEXT step's ground truth: uploaded from pinned memory on the other frame's copy stream while this
+            # step computes (a two-deep loader); it waits for that frame's previous replay to have read its buffer
+            e2e_frames[(i + 1) % 2].set_inputs(gt_u8=gt_pin[(i + 1) % 2])
             if i > 0:  # read the PREVIOUS step's loss: every step's result reaches the host inside the timed region
                 done[(i - 1) % 2].synchronize()
                 losses.append(float(e2e_frames[(i - 1) % 2].loss_host))
@@ -431,7 +442,6 @@ def main():
     else:
         from gaussianavatars_b200 import l1_loss_u8
 
-        gt_pin = [t.pin_memory() for t in gt_host]
         copy_stream = torch.cuda.Stream(device=dev)
         loss_host = [torch.zeros((), dtype=torch.float32).pin_memory() for _ in range(2)]
         loss_ready = [torch.cuda.Event() for _ in range(2)]
@@ -499,8 +509,12 @@ def main():
         for i in range(5):
             step_b3(i)
         ms_b3, launches_b3, _, _, _, _ = timed_pass(step_b3, False)
+        _, _, _, _, stage_b3, _ = timed_pass(step_b3, True)
+        lib_ms_b3 = sum(v[0] / max(v[1], 1) for v in stage_b3.values())
         R.set_exact_binning(args.exact_binning)
         b3 = {"value": K / (ms_b3 / 1e3), "unit": "frames/s", "ms_per_step": ms_b3 / K, "gpu_launches_per_step": launches_b3 / K,
+              "rasterizer_kernels_ms": lib_ms_b3, "eager_binding_and_autograd_ms": ms_b3 / K - lib_ms_b3,
+              "instances_per_frame": int(R.last_frame_info().get("num_rendered", 0)),
               "what": "SURVEY 8(d) baseline 3: the reference's eager binding getters (PyTorch ops on the GPU, autograd "
                       "through them) + this repo's UNFUSED operator surface + exact_binning=1 (the reference's full "
                       "3-sigma instance list), fwd+bwd, L2 flushed.  A structural proxy for the absent upstream "
@@ -608,6 +622,7 @@ def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gou
     t, tb = cpu_frames(params, verts, faces, cams_host, frames)
     sec = sum(t) / len(t)
     # SURVEY 8(d) baseline 2: the reference's PyTorch-only CPU transform path (binding getters), one thread
+    default_threads = torch.get_num_threads()
     torch.set_num_threads(1)
     b = params["binding"].long()
     tb1 = []
@@ -620,7 +635,7 @@ def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gou
         ob.get_opacity(params["_opacity"])
         ob.get_features(params["_features_dc"], params["_features_rest"])
         tb1.append(time.perf_counter() - t0)
-    torch.set_num_threads(cores)
+    torch.set_num_threads(default_threads)
     out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
                            "sample": f"{frames} full frames of the same workload (eager torch binding getters + "
                                      f"C oracle rasterizer fwd+bwd, OpenMP x{cores}); the port is the parity CHECKER "

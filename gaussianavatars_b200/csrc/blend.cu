@@ -419,6 +419,22 @@ __device__ __forceinline__ void visit_bands(PixState<K>& p, int pos, float py, f
   }
 }
 
+// Dead bands skipped with warp-uniform branches, live bands one after the other (template recursion keeps the band
+// index a compile-time constant, so p.X[i] stays in registers).
+template <int K, int I>
+struct BandLoop {
+  static __device__ __forceinline__ void run(uint32_t m, PixState<K>& p, int pos, float py, float tA, float dx, float Bp,
+                                             float Cp, float op, float cr, float cg, float cb, SplatSums& s) {
+    if (m & (1u << I)) visit_bands<K, (1 << I)>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+    BandLoop<K, I + 1>::run(m, p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+  }
+};
+template <int K>
+struct BandLoop<K, K> {
+  static __device__ __forceinline__ void run(uint32_t, PixState<K>&, int, float, float, float, float, float, float, float,
+                                             float, float, SplatSums&) {}
+};
+
 template <int K>
 __device__ __forceinline__ void visit_switch(uint32_t m, PixState<K>& p, int pos, float py, float tA, float dx,
                                              float Bp, float Cp, float op, float cr, float cg, float cb,
@@ -622,6 +638,225 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
   cp_async_wait<0>();
 }
 
+// =====================================================================================================
+// Backward, warp-independent form (variant 1..3 of GAB200_TUNE_BWD_VARIANT)
+// =====================================================================================================
+// Same pixel ownership and per-pair arithmetic as backward_tile above, different schedule:
+//   * a WARP is the unit of work: (tile, half, band group).  It stages its own id/mask lists (TMA bulk copies into a
+//     private 3-slot ring) and gathers only the records of entries that touch ITS blocks -- no CTA barrier anywhere,
+//     the two (four) warps of a tile drift apart freely, and each walks only up to ITS pixels' largest n_contrib.
+//   * the visit is one straight-line block (BANDS_ALWAYS: all K bands, dead lanes carry zeros) so the compiler can
+//     interleave the bands' chains with ...
+//   * ... a SOFTWARE-PIPELINED reduction: visit j stores its nine per-lane values as rows of a shared-memory tile;
+//     during visit j+1 eighteen lanes each add half a row (4 LDS.128) and store 18 partials; during visit j+2 nine
+//     lanes add the two halves and issue the RED.  No shuffle, no exposed shared-memory or shuffle latency: the
+//     loads of round 1/2 are issued at the top of a visit and consumed after its band math.
+#define BANDS_ALWAYS 1    // straight-line, every band every visit
+#define BANDS_UNIFORM 2   // each band under a warp-uniform branch (dead bands skipped, no interleaving)
+#define BANDS_HYBRID 3    // all bands live: straight-line; otherwise as BANDS_UNIFORM
+
+#define ROWS_STRIDE 36
+#define ROWS_WORDS (9 * ROWS_STRIDE)
+struct __align__(16) WarpSmem {
+  SplatRec rec[2][32];
+  float rows[2][ROWS_WORDS];        // [visit parity][component][lane], row stride 36 floats
+  float part[2][32];                // [visit parity][component * 2 + half]  (18 used)
+  uint32_t ids[ID_RING][32 + 4];
+  uint8_t masks[ID_RING][32 + 16];
+  uint64_t mbar[ID_RING];
+};
+
+template <int K, int MODE>
+__device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, int W, int H, int gx,
+                                              const uint2* __restrict__ ranges,
+                                              const uint32_t* __restrict__ point_list,
+                                              const SplatRec* __restrict__ rec, const float* __restrict__ bg,
+                                              const float* __restrict__ final_T,
+                                              const uint32_t* __restrict__ n_contrib,
+                                              const float* __restrict__ dL_dpix,
+                                              const uint8_t* __restrict__ strip_mask, float* __restrict__ g2d) {
+  const int tx = tile % gx, ty = tile / gx;
+  const int lane = tl & 31;
+  const BandGeom<K> geo(tl);
+  const int pixx = tx * GAB_TILE + geo.col;
+  const int pixy0 = ty * GAB_TILE + geo.row0;
+  const float fx = (float)pixx;
+  const uint2 range = ranges[tile];
+  const size_t HW = (size_t)H * W;
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+
+  PixState<K> p;
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < K; i++) {
+    const int y = pixy0 + 4 * i;
+    p.fy[i] = (float)y;
+    p.ar[i] = p.ag[i] = p.ab[i] = 0.f;
+    if (pixx < W && y < H) {
+      const size_t pix = (size_t)y * W + pixx;
+      p.T[i] = final_T[pix];
+      p.nc[i] = (int)n_contrib[pix];
+      p.dr[i] = dL_dpix[pix];
+      p.dg[i] = dL_dpix[HW + pix];
+      p.db[i] = dL_dpix[2 * HW + pix];
+    } else {
+      p.T[i] = 0.f; p.nc[i] = 0; p.dr[i] = p.dg[i] = p.db[i] = 0.f;
+    }
+    p.bgT[i] = p.T[i] * (bg0 * p.dr[i] + bg1 * p.dg[i] + bg2 * p.db[i]);
+    n = max(n, p.nc[i]);
+  }
+  // this warp only needs instances [0, max n_contrib of ITS pixels)
+  n = __reduce_max_sync(FULLMASK, n);
+  if (n == 0) return;
+  const int nchunks = (n + 31) >> 5;
+  const float half_W = 0.5f * (float)W, half_H = 0.5f * (float)H;
+
+  constexpr uint32_t TX_BYTES = (32 + 4) * 4 + (32 + 16);
+  auto chunk_lo = [&](int k) { return max(0, n - (k + 1) * 32); };
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < ID_RING; k++) mbar_init(&sm.mbar[k], 1);
+    mbar_fence_init();
+  }
+  __syncwarp();
+  auto issue_lists = [&](int k) {
+    const uint32_t lo = range.x + (uint32_t)chunk_lo(k);
+    uint64_t* b = &sm.mbar[k % ID_RING];
+    mbar_arrive_expect_tx(b, TX_BYTES);
+    bulk_copy_g2s(sm.ids[k % ID_RING], point_list + (lo & ~3u), (32 + 4) * 4, b);
+    bulk_copy_g2s(sm.masks[k % ID_RING], strip_mask + (lo & ~15u), 32 + 16, b);
+  };
+  const int bit0 = geo.bit(0);
+  // entry of chunk k owned by this lane: reverse index q = 32 k + lane <-> list position n-1-q
+  auto stage_chunk = [&](int k, uint32_t& id, uint32_t& mine) {
+    mbar_wait(&sm.mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1));
+    const int q = k * 32 + lane;
+    id = 0xffffffffu;
+    mine = 0u;
+    if (q < n) {
+      const int lo = chunk_lo(k);
+      const uint32_t g0 = range.x + (uint32_t)lo;
+      const int rel = (n - 1 - q) - lo;
+      id = sm.ids[k % ID_RING][(int)(g0 & 3u) + rel];
+      const uint32_t mask = sm.masks[k % ID_RING][(int)(g0 & 15u) + rel];
+#pragma unroll
+      for (int i = 0; i < K; i++) mine |= ((mask >> (bit0 + 2 * i)) & 1u) << i;
+      if (mine) gather_rec(&sm.rec[k & 1][lane], rec + id);
+    }
+    cp_async_commit();
+  };
+  if (lane == 0) {
+    issue_lists(0);
+    if (nchunks > 1) issue_lists(1);
+  }
+  uint32_t id_c, mine_c, id_n = 0xffffffffu, mine_n = 0u;
+  stage_chunk(0, id_c, mine_c);
+
+  // reduction pipeline state: ids of the two visits whose sums are still on their way out
+  uint32_t id1 = 0xffffffffu, id2 = 0xffffffffu;  // visit j-1 (rows written), visit j-2 (partials written)
+  uint32_t par = 0;                                // parity of the current visit
+  // round 1 (lane < 18): component c1 = lane / 2, half h1 = lane & 1: sum of rows[c1][16 h1 .. 16 h1 + 15]
+  const int c1 = min(lane >> 1, 8), h1 = lane & 1;
+  // round 2 (lane < 9): component lane: part[2 lane] + part[2 lane + 1]
+  auto reduce_step = [&](uint32_t id_rows, uint32_t id_part) {
+    // partials of the visit before last -> global
+    const float2 pp = *reinterpret_cast<const float2*>(&sm.part[par][2 * min(lane, 8)]);
+    // rows of the last visit -> partials
+    const float4* r4 = reinterpret_cast<const float4*>(&sm.rows[par ^ 1][c1 * ROWS_STRIDE + h1 * 16]);
+    const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
+    if (id_part != 0xffffffffu && lane < 9) atomicAdd(g2d + (size_t)id_part * GAB_G2D_STRIDE + lane, pp.x + pp.y);
+    const float s = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
+                    (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    if (id_rows != 0xffffffffu && lane < 18) sm.part[par ^ 1][lane] = s;
+  };
+
+  for (int c = 0; c < nchunks; c++) {
+    __syncwarp();  // every lane is done with the record buffer and ring slot the next two lines overwrite
+    if (c + 1 < nchunks) stage_chunk(c + 1, id_n, mine_n);  // its ids arrived while chunk c-1 was walked
+    else cp_async_commit();
+    if (lane == 0 && c + 2 < nchunks) issue_lists(c + 2);   // ring slot (c+2)%3 was last read for chunk c-1
+    cp_async_wait<1>();
+    __syncwarp();
+    const SplatRec* cur = sm.rec[c & 1];
+    uint32_t todo = __ballot_sync(FULLMASK, mine_c != 0u);
+    while (todo) {
+      const int jj = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const uint32_t m = __shfl_sync(FULLMASK, mine_c, jj);
+      const uint32_t id0 = __shfl_sync(FULLMASK, id_c, jj);
+      const int pos = n - 1 - (c * 32 + jj);
+      __syncwarp();  // rows/partials of the previous visit are complete; this visit's buffers are free
+      const float4 q0 = cur[jj].q0;
+      const float4 q1 = cur[jj].q1;
+      const float cbl = cur[jj].q2.x;
+      reduce_step(id1, id2);
+      const float dx = q0.x - fx;
+      const float tA = q0.z * dx;
+      SplatSums s;
+      s.S0 = s.S1 = s.S2 = s.go = s.gr = s.gg = s.gb = 0.f;
+      if (MODE == BANDS_ALWAYS || (MODE == BANDS_HYBRID && m == (1u << K) - 1u)) {
+        visit_bands<K, (1 << K) - 1>(p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
+      } else {
+        BandLoop<K, 0>::run(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
+      }
+      const float A = q0.z * CONIC_UNSCALE_AC, B = q0.w * CONIC_UNSCALE_B, C = q1.x * CONIC_UNSCALE_AC;
+      const float dxS0 = dx * s.S0;
+      float* row = &sm.rows[par][lane];
+      row[0 * ROWS_STRIDE] = (-A * dxS0 - B * s.S1) * half_W;  // dL/dmean2D.x (NDC units)
+      row[1 * ROWS_STRIDE] = (-C * s.S1 - B * dxS0) * half_H;  // dL/dmean2D.y
+      row[2 * ROWS_STRIDE] = -0.5f * dx * dxS0;                // dL/dconic.xx
+      row[3 * ROWS_STRIDE] = -0.5f * dx * s.S1;                // dL/dconic.xy (stored once)
+      row[4 * ROWS_STRIDE] = -0.5f * s.S2;                     // dL/dconic.yy
+      row[5 * ROWS_STRIDE] = s.go;                             // dL/dopacity
+      row[6 * ROWS_STRIDE] = s.gr;
+      row[7 * ROWS_STRIDE] = s.gg;
+      row[8 * ROWS_STRIDE] = s.gb;
+      id2 = id1;
+      id1 = id0;
+      par ^= 1;
+    }
+    id_c = id_n;
+    mine_c = mine_n;
+  }
+  cp_async_wait<0>();
+  // drain the reduction pipeline: two more steps
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    __syncwarp();
+    reduce_step(id1, id2);
+    id2 = id1;
+    id1 = 0xffffffffu;
+    par ^= 1;
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(128, 4) blend_backward_warp_kernel(int W, int H, int gx, int tiles,
+                                                                      const uint2* __restrict__ ranges,
+                                                                      const uint32_t* __restrict__ order,
+                                                                      const uint32_t* __restrict__ order_info,
+                                                                      const uint32_t* __restrict__ point_list,
+                                                                      const SplatRec* __restrict__ rec,
+                                                                      const float* __restrict__ bg,
+                                                                      const float* __restrict__ final_T,
+                                                                      const uint32_t* __restrict__ n_contrib,
+                                                                      const float* __restrict__ dL_dpix,
+                                                                      const uint8_t* __restrict__ strip_mask,
+                                                                      float* __restrict__ g2d) {
+  __shared__ WarpSmem sm[4];
+  const int nh = (int)order_info[1];
+  const int b = blockIdx.x, t = threadIdx.x, w = t >> 5;
+  if (b < nh) {  // heavy tile: four warps, two bands each
+    backward_task<2, MODE>((int)order[b], t, sm[w], W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib, dL_dpix,
+                           strip_mask, g2d);
+  } else {       // two light tiles: two warps (the halves) each, four bands per warp
+    const int slot = nh + 2 * (b - nh) + (w >> 1);
+    if (slot >= tiles) return;
+    backward_task<4, MODE>((int)order[slot], t & 63, sm[w], W, H, gx, ranges, point_list, rec, bg, final_T, n_contrib,
+                           dL_dpix, strip_mask, g2d);
+  }
+}
+
 #ifndef BWD_MIN_BLOCKS
 #define BWD_MIN_BLOCKS 4
 #endif
@@ -670,8 +905,23 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
-  blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
-                                                   final_T, n_contrib, dL_dpix, strip_mask, g2d);
+  switch (tune_get(GAB200_TUNE_BWD_VARIANT)) {
+    case 1:
+      blend_backward_warp_kernel<BANDS_ALWAYS><<<tiles, 128, 0, stream>>>(
+          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+      break;
+    case 2:
+      blend_backward_warp_kernel<BANDS_UNIFORM><<<tiles, 128, 0, stream>>>(
+          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+      break;
+    case 3:
+      blend_backward_warp_kernel<BANDS_HYBRID><<<tiles, 128, 0, stream>>>(
+          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
+      break;
+    default:
+      blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
+                                                       final_T, n_contrib, dL_dpix, strip_mask, g2d);
+  }
   count_launch();
 }
 

@@ -58,8 +58,10 @@ class GraphedFrame:
                  headroom: float = 1.5, after_backward=None, warm_cameras=None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
-        host_inputs: the graph starts with H2D copies out of the pinned staging tensors `cam_host` / `gt_host`
-        (the ground truth on a side branch that overlaps the forward) and ends with a D2H copy of the loss to `loss_host`.
+        host_inputs: the graph starts with an H2D copy of the camera block out of the pinned staging tensor `cam_host`
+        and ends with a D2H copy of the loss to `loss_host`; a ground truth handed to `set_inputs(gt_u8=<pinned host
+        tensor>)` is uploaded on this frame's own copy stream (it may run under the previous replay; `run()` makes
+        the replay wait for it on the GPU).
         after_backward: optional callable run inside the capture after backward (e.g. the gradient all-reduce).
         warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity."""
         if loss not in ("l1_u8", "photometric", "dL_dimage"):
@@ -77,8 +79,7 @@ class GraphedFrame:
         self.gt = torch.zeros((3, self.H, self.W), dtype=torch.uint8, device=dev) if loss != "dL_dimage" else None
         self.dL_dimage = torch.zeros((3, self.H, self.W), dtype=torch.float32, device=dev) if loss == "dL_dimage" else None
         self.cam_host = torch.zeros(35, dtype=torch.float32).pin_memory() if host_inputs else None
-        self.gt_host = (torch.zeros((3, self.H, self.W), dtype=torch.uint8).pin_memory()
-                        if host_inputs and self.gt is not None else None)
+        self._gt_ready = self._done = None   # events ordering the ground-truth upload against the replays
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self.loss = None
         self.image = self.radii = self.viewspace_points = None
@@ -100,7 +101,17 @@ class GraphedFrame:
             with torch.no_grad():
                 self.verts.copy_(verts.reshape(self.verts.shape), non_blocking=True)
         if gt_u8 is not None:
-            (self.gt_host if self.host_inputs else self.gt).copy_(gt_u8, non_blocking=True)
+            if gt_u8.device.type == "cpu" and self._side is not None:
+                # upload on the copy stream: after the last replay that read self.gt, concurrently with whatever the
+                # main stream is running now
+                if self._done is not None:
+                    self._side.wait_event(self._done)
+                with torch.cuda.stream(self._side):
+                    self.gt.copy_(gt_u8, non_blocking=True)
+                    self._gt_ready = torch.cuda.Event()
+                    self._gt_ready.record(self._side)
+            else:
+                self.gt.copy_(gt_u8, non_blocking=True)
         if dL_dimage is not None:
             self.dL_dimage.copy_(dL_dimage, non_blocking=True)
 
@@ -113,17 +124,10 @@ class GraphedFrame:
         for p in self._params():
             p.grad = None
         self.verts.grad = None
-        cur = torch.cuda.current_stream(self.device)
         if self.host_inputs:
             self.cam.copy_(self.cam_host, non_blocking=True)
-            if self.gt_host is not None:  # side branch: the 6 MB upload overlaps the forward
-                self._side.wait_stream(cur)
-                with torch.cuda.stream(self._side):
-                    self.gt.copy_(self.gt_host, non_blocking=True)
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
-        if self.host_inputs and self.gt_host is not None:
-            cur.wait_stream(self._side)
         img = out["render"]
         if self.loss_kind == "l1_u8":
             loss = l1_loss_u8(img, self.gt)
@@ -195,8 +199,14 @@ class GraphedFrame:
     def run(self, check: bool = False):
         if self.graph is None:
             self.capture()
+        if self._gt_ready is not None:   # a ground-truth upload is in flight on the copy stream
+            torch.cuda.current_stream(self.device).wait_event(self._gt_ready)
+            self._gt_ready = None
         self.graph.replay()
         self.replays += 1
+        if self._side is not None:
+            self._done = torch.cuda.Event()
+            self._done.record()
         for p, g in zip(self._params(), self.grads):
             p.grad = g
         self.pc.flat_grad = self.flat_grad

@@ -82,8 +82,11 @@ def _compare(cuda, ref, what):
     # R_face R(q) (fused) and R(q_face (x) q) (eager) round differently: a handful of ceil() knife edges in the radius
     assert n_r <= max(3, 1e-3 * cuda["radii"].size), f"{what}: {n_r} radii differ"
     h.assert_image_close(cuda["image"], ref["image"], what + " image", frac=2e-4)
-    for k in ("_xyz", "_rotation", "_scaling", "_opacity", "_features_dc", "_features_rest", "means2D", "verts"):
+    for k in ("_xyz", "_rotation", "_scaling", "_opacity", "_features_dc", "_features_rest", "means2D"):
         h.assert_grad_tight(cuda["grads"][k], ref["grads"][k], f"{what} dL/d{k}")
+    # a vertex gradient is the sum of 13 face-frame terms x 3 faces x every splat bound to them (hundreds of fp32
+    # additions with cancellation, against the oracle's float64): absolute floor 1e-4 of the tensor's maximum
+    h.assert_grad_tight(cuda["grads"]["verts"], ref["grads"]["verts"], f"{what} dL/dverts", atol_frac=1e-4)
 
 
 @pytest.mark.parametrize("cam_index", [0, 11])
