@@ -170,6 +170,15 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on the host cores (bench.py's cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------
+def host_cpus():
+    """CPUs this process may run on (the affinity mask of the container, not the machine's os.cpu_count(): forcing 128
+    OpenMP threads onto a smaller mask made the CPU arm 10x slower)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def cpu_frames(params, verts, faces, cams, frames, threads=None):
     """Runs `frames` full fwd+bwd frames of the same workload through the CPU oracle (eager torch binding getters +
     C rasterizer, OpenMP over all host cores).  Returns (seconds per frame list, binding seconds per frame list)."""
@@ -182,7 +191,7 @@ def cpu_frames(params, verts, faces, cams, frames, threads=None):
     # The C oracle (its own libgomp) gets every logical CPU; torch's intra-op pool keeps its default (one thread per
     # physical core) unless the launcher forced it to 1 -- two pools of spinning threads on every logical CPU
     # oversubscribe the box (measured: the eager binding getters went from 19 ms to 3.5 s per frame).
-    cpus = os.cpu_count() or 1
+    cpus = host_cpus()
     orc.set_threads(threads or cpus)
     if threads:
         torch.set_num_threads(threads)
@@ -226,7 +235,7 @@ def run_reference(args, rank, world):
     verts, faces = syn.head_mesh()
     params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
     cams = make_cameras(N_CAMERAS)
-    cores = os.cpu_count() or 1
+    cores = host_cpus()
     # bounded sample: one frame per step, steps capped so the whole run stays within ~2 minutes
     steps = max(1, min(args.steps, 12))
     warm = max(1, min(args.warmup, 2))
@@ -616,7 +625,7 @@ def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gou
     from oracle import fused_reference as fr
 
     out = {}
-    cores = os.cpu_count() or 1
+    cores = host_cpus()
     cpu_frames(params, verts, faces, cams_host, 1)
     frames = 6
     t, tb = cpu_frames(params, verts, faces, cams_host, frames)
@@ -640,6 +649,7 @@ def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gou
                            "sample": f"{frames} full frames of the same workload (eager torch binding getters + "
                                      f"C oracle rasterizer fwd+bwd, OpenMP x{cores}); the port is the parity CHECKER "
                                      "being timed (scalar C, one tile per task), not a tuned CPU renderer",
+                           "machine_cpus": os.cpu_count(), "torch_threads": default_threads,
                            "binding_ms_per_frame": 1e3 * sum(tb) / len(tb),
                            "binding_ms_per_frame_1thread": 1e3 * sorted(tb1)[len(tb1) // 2]}
     # parity of the benchmarked frame

@@ -654,6 +654,7 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
 #define BANDS_ALWAYS 1    // straight-line, every band every visit
 #define BANDS_UNIFORM 2   // each band under a warp-uniform branch (dead bands skipped, no interleaving)
 #define BANDS_HYBRID 3    // all bands live: straight-line; otherwise as BANDS_UNIFORM
+#define BANDS_SWITCH 4    // one straight-line body per live-band set (visit_switch)
 
 #define ROWS_STRIDE 36
 #define ROWS_WORDS (9 * ROWS_STRIDE)
@@ -796,6 +797,8 @@ __device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, in
       s.S0 = s.S1 = s.S2 = s.go = s.gr = s.gg = s.gb = 0.f;
       if (MODE == BANDS_ALWAYS || (MODE == BANDS_HYBRID && m == (1u << K) - 1u)) {
         visit_bands<K, (1 << K) - 1>(p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
+      } else if (MODE == BANDS_SWITCH) {
+        visit_switch<K>(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
       } else {
         BandLoop<K, 0>::run(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
       }
@@ -830,8 +833,8 @@ __device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, in
   }
 }
 
-template <int MODE>
-__global__ void __launch_bounds__(128, 4) blend_backward_warp_kernel(int W, int H, int gx, int tiles,
+template <int MODE, int MINB>
+__global__ void __launch_bounds__(128, MINB) blend_backward_warp_kernel(int W, int H, int gx, int tiles,
                                                                       const uint2* __restrict__ ranges,
                                                                       const uint32_t* __restrict__ order,
                                                                       const uint32_t* __restrict__ order_info,
@@ -905,23 +908,23 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
+#define GAB_BWD_WARP(MODE, MINB)                                                                                  \
+  blend_backward_warp_kernel<MODE, MINB><<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info,      \
+                                                                    point_list, rec, bg, final_T, n_contrib, dL_dpix, \
+                                                                    strip_mask, g2d)
   switch (tune_get(GAB200_TUNE_BWD_VARIANT)) {
-    case 1:
-      blend_backward_warp_kernel<BANDS_ALWAYS><<<tiles, 128, 0, stream>>>(
-          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
-      break;
-    case 2:
-      blend_backward_warp_kernel<BANDS_UNIFORM><<<tiles, 128, 0, stream>>>(
-          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
-      break;
-    case 3:
-      blend_backward_warp_kernel<BANDS_HYBRID><<<tiles, 128, 0, stream>>>(
-          W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg, final_T, n_contrib, dL_dpix, strip_mask, g2d);
-      break;
+    case 1: GAB_BWD_WARP(BANDS_ALWAYS, 4); break;
+    case 2: GAB_BWD_WARP(BANDS_UNIFORM, 4); break;
+    case 3: GAB_BWD_WARP(BANDS_HYBRID, 4); break;
+    case 4: GAB_BWD_WARP(BANDS_HYBRID, 5); break;
+    case 5: GAB_BWD_WARP(BANDS_UNIFORM, 5); break;
+    case 6: GAB_BWD_WARP(BANDS_SWITCH, 4); break;
+    case 7: GAB_BWD_WARP(BANDS_UNIFORM, 6); break;
     default:
       blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
                                                        final_T, n_contrib, dL_dpix, strip_mask, g2d);
   }
+#undef GAB_BWD_WARP
   count_launch();
 }
 
