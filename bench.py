@@ -430,17 +430,19 @@ def main():
             f_.capture()
             e2e_frames.append(f_)
         done = [torch.cuda.Event() for _ in range(2)]
-        e2e_frames[0].set_inputs(gt_u8=gt_pin[0])   # the first step's ground truth is on its way before the clock starts
+        # the first step's inputs are on their way before the clock starts
+        e2e_frames[0].set_inputs(camera=cam_host_blocks[0], gt_u8=gt_pin[0])
 
         def step_e2e(i):
             f_ = e2e_frames[i % 2]
-            f_.cam_host.copy_(cam_host_blocks[i % len(cam_host_blocks)])   # 140-byte host write into pinned staging
             f_.set_inputs(verts=posed[i % len(posed)].detach())
-            f_.run()                                                        # waits (on the GPU) for this step's upload
+            f_.run()                                                        # waits (on the GPU) for this step's uploads
             done[i % 2].record()
-            # the NEXT step's ground truth: uploaded from pinned memory on the other frame's copy stream while this
-            # step computes (a two-deep loader); it waits for that frame's previous replay to have read its buffer
-            e2e_frames[(i + 1) % 2].set_inputs(gt_u8=gt_pin[(i + 1) % 2])
+            # the NEXT step's camera block and ground truth: uploaded from pinned memory on the other frame's copy
+            # stream while this step computes (a two-deep loader); the uploads wait for that frame's previous replay
+            # to have read its buffers
+            e2e_frames[(i + 1) % 2].set_inputs(camera=cam_host_blocks[(i + 1) % len(cam_host_blocks)],
+                                               gt_u8=gt_pin[(i + 1) % 2])
             if i > 0:  # read the PREVIOUS step's loss: every step's result reaches the host inside the timed region
                 done[(i - 1) % 2].synchronize()
                 losses.append(float(e2e_frames[(i - 1) % 2].loss_host))

@@ -58,10 +58,12 @@ class GraphedFrame:
                  headroom: float = 1.5, after_backward=None, warm_cameras=None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
-        host_inputs: the graph starts with an H2D copy of the camera block out of the pinned staging tensor `cam_host`
-        and ends with a D2H copy of the loss to `loss_host`; a ground truth handed to `set_inputs(gt_u8=<pinned host
-        tensor>)` is uploaded on this frame's own copy stream (it may run under the previous replay; `run()` makes
-        the replay wait for it on the GPU).
+        host_inputs: inputs handed to `set_inputs()` as (pinned) HOST tensors -- camera block, ground truth -- are
+        uploaded on this frame's own copy stream, where they may run under whatever the main stream is doing (e.g. the
+        previous step, with two frames used alternately); `run()` makes the replay wait for them ON THE GPU, and the
+        graph ends with a D2H copy of the loss to `loss_host`.  (No H2D node sits inside the graph: measured, a
+        140-byte camera copy at the head of the graph queued on the copy engine behind the 6 MB ground truth of the
+        NEXT step and delayed every replay by the full 124 us of that transfer.)
         after_backward: optional callable run inside the capture after backward (e.g. the gradient all-reduce).
         warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity."""
         if loss not in ("l1_u8", "photometric", "dL_dimage"):
@@ -78,7 +80,7 @@ class GraphedFrame:
         self.verts = pc.verts_rest.detach().clone().contiguous().requires_grad_(True)
         self.gt = torch.zeros((3, self.H, self.W), dtype=torch.uint8, device=dev) if loss != "dL_dimage" else None
         self.dL_dimage = torch.zeros((3, self.H, self.W), dtype=torch.float32, device=dev) if loss == "dL_dimage" else None
-        self.cam_host = torch.zeros(35, dtype=torch.float32).pin_memory() if host_inputs else None
+        self.cam_host = torch.zeros(35, dtype=torch.float32).pin_memory() if host_inputs else None  # staging
         self._gt_ready = self._done = None   # events ordering the ground-truth upload against the replays
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self.loss = None
@@ -96,24 +98,33 @@ class GraphedFrame:
         """Copies new inputs into the static buffers (device tensors) / staging buffers (host_inputs)."""
         if camera is not None:
             blk = camera if isinstance(camera, torch.Tensor) else camera_block(camera)
-            (self.cam_host if self.host_inputs else self.cam).copy_(blk, non_blocking=True)
+            if blk.device.type == "cpu" and self._side is not None:
+                if not blk.is_pinned():      # stage pageable memory (after any upload still reading the staging copy)
+                    self._side.synchronize()
+                    self.cam_host.copy_(blk)
+                    blk = self.cam_host
+                self._upload(self.cam, blk)
+            else:
+                self.cam.copy_(blk, non_blocking=True)
         if verts is not None:
             with torch.no_grad():
                 self.verts.copy_(verts.reshape(self.verts.shape), non_blocking=True)
         if gt_u8 is not None:
             if gt_u8.device.type == "cpu" and self._side is not None:
-                # upload on the copy stream: after the last replay that read self.gt, concurrently with whatever the
-                # main stream is running now
-                if self._done is not None:
-                    self._side.wait_event(self._done)
-                with torch.cuda.stream(self._side):
-                    self.gt.copy_(gt_u8, non_blocking=True)
-                    self._gt_ready = torch.cuda.Event()
-                    self._gt_ready.record(self._side)
+                self._upload(self.gt, gt_u8)
             else:
                 self.gt.copy_(gt_u8, non_blocking=True)
         if dL_dimage is not None:
             self.dL_dimage.copy_(dL_dimage, non_blocking=True)
+
+    def _upload(self, dst, src_host):
+        """H2D on the copy stream: after the last replay that read `dst`, concurrently with the main stream."""
+        if self._done is not None:
+            self._side.wait_event(self._done)
+        with torch.cuda.stream(self._side):
+            dst.copy_(src_host, non_blocking=True)
+            self._gt_ready = torch.cuda.Event()
+            self._gt_ready.record(self._side)
 
     # ---- the step body (run eagerly for warm-up, then captured) --------------------------------------------------
     def _params(self):
@@ -124,8 +135,6 @@ class GraphedFrame:
         for p in self._params():
             p.grad = None
         self.verts.grad = None
-        if self.host_inputs:
-            self.cam.copy_(self.cam_host, non_blocking=True)
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
         img = out["render"]
@@ -151,7 +160,7 @@ class GraphedFrame:
         hints = R.hints_of(self.pc)
         key = (self.device, self.W, self.H, self.pc._xyz.shape[0])
         n_max, lo, hi = 0, 0xFFFFFFFF, 0
-        blocks = self._warm if self._warm else [self.cam_host.clone() if self.host_inputs else self.cam.clone()]
+        blocks = self._warm if self._warm else [self.cam.clone()]
         # eager frames on a side stream (torch's recipe for whole-step capture): nothing autograd creates here may be
         # tied to the legacy default stream
         cur = torch.cuda.current_stream(self.device)
@@ -160,7 +169,7 @@ class GraphedFrame:
         with torch.cuda.stream(side):
             for rep in range(2):
                 for blk in blocks:
-                    (self.cam_host if self.host_inputs else self.cam).copy_(blk)
+                    self.cam.copy_(blk)
                     self._body()
                     info = hints.last or {}
                     n_max = max(n_max, int(info.get("num_rendered", 0)))

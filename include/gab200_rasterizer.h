@@ -334,12 +334,15 @@ int32_t gab200_stage_times(double total_ms[GAB200_NUM_STAGES], int64_t launches[
  * gab200_tune(knob, value) sets a knob and returns the previous value; value < 0 only queries. */
 enum {
   GAB200_TUNE_HEAVY_FWD = 0,   /* forward blend: a tile is "heavy" (1 px/thread, 8 warps) from this list length (default 32) */
-  GAB200_TUNE_HEAVY_BWD = 1,   /* backward blend: a tile is "heavy" (K = 2, 4 warps) from this list length (default 1024) */
+  GAB200_TUNE_HEAVY_BWD = 1,   /* backward blend: a tile is "heavy" (K = 2, 4 warps) from this list length (default 2048) */
   GAB200_TUNE_DEPTH_SORT = 2,  /* 0 (default): bucket sort when a depth hint is given; 1: always cub radix sort */
   GAB200_TUNE_BWD_VARIANT = 3, /* backward blend schedule (same arithmetic, same results up to summation order):
                                   0 tile = CTA group, live-band-set specialised bodies; 1 warp-independent tasks,
-                                  straight-line bands, pipelined reduction; 2 / 3 as 1 with dead bands skipped by
-                                  uniform branches always / unless all bands are live */
+                                  straight-line bands, pipelined reduction; 2 / 3 (default) as 1 with dead bands
+                                  skipped by uniform branches always / unless all bands are live; 4, 5 = 3, 2 compiled
+                                  for 5 CTAs per SM; 6 = 1 with specialised bodies; 7 = 2 for 6 CTAs per SM.
+                                  Measured at the headline size (profiles/r02/bwd_variants.jsonl): 211 / 198 / 179 /
+                                  175 / 182 / 185 / 186 / 211 us */
   GAB200_NUM_TUNABLES = 8
 };
 int32_t gab200_tune(int32_t knob, int32_t value);
