@@ -20,7 +20,7 @@ INPUT_BOUND_RAW = 1
 SYNC_EXACT, SYNC_LATE, SYNC_NONE = 0, 1, 2
 CTR_NOT_MIN_DEPTH_KEY, CTR_MAX_DEPTH_KEY, CTR_NUM_RENDERED, CTR_NUM_LISTED, CTR_BUCKET_OVERFLOW, CTR_CAPACITY, CTR_SEQ = range(7)
 NUM_COUNTERS = 8
-TUNE_HEAVY_FWD, TUNE_HEAVY_BWD, TUNE_DEPTH_SORT, TUNE_BWD_VARIANT = 0, 1, 2, 3
+TUNE_HEAVY_FWD, TUNE_HEAVY_BWD, TUNE_DEPTH_SORT, TUNE_BWD_VARIANT, TUNE_TILE_SORT = 0, 1, 2, 3, 4
 
 ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 
@@ -53,7 +53,8 @@ class FrameState(C.Structure):
         ("sorted_selector", C.c_int32), ("sort_bits", C.c_int32), ("depth_bits", C.c_int32),
         ("depth_prefix", C.c_uint32), ("binning_capacity", C.c_int64),
         ("depth_key_min", C.c_uint32), ("depth_key_max", C.c_uint32), ("depth_sort_path", C.c_int32),
-        ("attempts", C.c_int32), ("device_counters", C.c_void_p),
+        ("attempts", C.c_int32), ("tile_sort_path", C.c_int32), ("reserved0", C.c_int32),
+        ("device_counters", C.c_void_p),
     ]
 
 

@@ -24,6 +24,7 @@ SOURCES = {
     "preprocess.cu": ["--fmad=false"],
     "preprocess_bwd.cu": [],
     "binning.cu": [],
+    "tile_sort.cu": [],
     "blend.cu": [],
     "face_frame.cu": [],
     "loss.cu": [],

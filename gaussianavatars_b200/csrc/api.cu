@@ -127,6 +127,8 @@ struct ImageView {
   uint2* ranges;
   uint32_t* order;
   uint32_t* order_info;
+  uint32_t* tile_count;   // counting tile sort: instances per tile (RED by preprocess), zeroed before it
+  uint32_t* tile_cursor;  //                     next free slot of the tile's segment (emission)
   float* final_T;
   uint32_t* n_contrib;
   size_t bytes;
@@ -138,6 +140,8 @@ static ImageView carve_image(void* base, int W, int H, bool need_backward) {
   v.ranges = c.take<uint2>((size_t)gx * gy + 1);  // + 1: the slot the sentinel key of a capacity-padded sort maps to
   v.order = c.take<uint32_t>((size_t)gx * gy);
   v.order_info = c.take<uint32_t>(4);
+  v.tile_count = c.take<uint32_t>((size_t)gx * gy);
+  v.tile_cursor = c.take<uint32_t>((size_t)gx * gy);
   v.final_T = need_backward ? c.take<float>((size_t)W * H) : nullptr;
   v.n_contrib = need_backward ? c.take<uint32_t>((size_t)W * H) : nullptr;
   v.bytes = c.bytes();
@@ -216,7 +220,7 @@ static int check_arch() {
 
 // tuning knobs (gab200_tune)
 static std::atomic<int> g_tune[GAB200_NUM_TUNABLES];
-static const int g_tune_default[GAB200_NUM_TUNABLES] = {32, 2048, 0, 3, 0, 0, 0, 0};
+static const int g_tune_default[GAB200_NUM_TUNABLES] = {32, 2048, 0, 3, 0, 0, 0, 0};  // see GAB200_TUNE_*
 int tune_get(int knob) {
   const int v = g_tune[knob].load(std::memory_order_relaxed);
   return v > 0 ? v - 1 : g_tune_default[knob];  // stored biased by one so that zero-initialised = "default"
@@ -341,6 +345,8 @@ struct Frame {
   cudaEvent_t ctr_event;
   int selA = 0;                           // which half of the stage-A double buffer holds the depth order
   const uint32_t* order_count = nullptr;  // device count of listed splats (bucket path), else all P are listed
+  bool counting = true;                   // tile sort: counting sort + per-tile rank sort (tile_sort.cu), else cub radix
+  uint32_t scan_clamp = 0xffffffffu;      // capacity the tile ranges were cut at by the last tile scan
 };
 
 // preprocess (+ bucket bookkeeping when `bucket`) -> per-splat depth order + emission offsets -> counters published
@@ -357,13 +363,23 @@ int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capaci
     d.scale = (float)((double)d.nb / ((double)(d.hi - d.lo) + 1.0));
     d.enabled = 1;
   }
+  const int tiles = f.gx * f.gy;
   if (run_preprocess) {
     GAB_CUDA(cudaMemsetAsync(d.counts, 0, g.bucket_clear_bytes, stream));
+    if (f.counting) GAB_CUDA(cudaMemsetAsync(f.iv.tile_count, 0, sizeof(uint32_t) * (size_t)tiles, stream));
     StageScope sc(GAB200_STAGE_PREPROCESS, stream);
     launch_preprocess(*a, g.rec, g.aux, g.tiles_touched, f.nb ? g.clamped : nullptr, g.depth_keys[0], g.ids[0], g.buckets,
-                      stream);
+                      f.counting ? f.iv.tile_count : nullptr, stream);
   }
   GAB_STAGE_CHECK(f.dbg, stream);
+  if (f.counting && run_preprocess) {
+    // tile ranges, write cursors, N and the heaviest-first tile order straight from the per-tile counts
+    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+    f.scan_clamp = capacity > 0 ? capacity : 0xffffffffu;
+    launch_tile_scan_order(tiles, f.iv.tile_count, f.scan_clamp, f.iv.ranges, f.iv.tile_cursor, f.iv.order,
+                           f.iv.order_info, g.buckets.meta, tune_get(GAB200_TUNE_HEAVY_FWD),
+                           tune_get(GAB200_TUNE_HEAVY_BWD), stream);
+  }
   {
     StageScope sc(GAB200_STAGE_SCAN, stream);
     if (bucket) {
@@ -375,11 +391,12 @@ int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capaci
       // stage A of the key sort (per splat, by depth) + emission offsets in depth order  -- see binning.cu
       GAB_CUDA(run_sort(g.sortA_temp, g.sortA_temp_bytes, g.depth_keys[0], g.depth_keys[1], g.ids[0], g.ids[1], f.P, 32,
                         &f.selA, stream));
-      GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[f.selA], g.tiles_touched, g.offsets, f.P, stream));
+      if (!f.counting)  // emission offsets in depth order: only the radix tile sort places instances by them
+        GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[f.selA], g.tiles_touched, g.offsets, f.P, stream));
       f.order_count = nullptr;
     }
-    launch_publish_counters(g.buckets.meta, bucket ? nullptr : g.offsets, f.P, capacity, a->frame_seq,
-                            a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr, stream);
+    launch_publish_counters(g.buckets.meta, (bucket || f.counting) ? nullptr : g.offsets, bucket ? 0 : f.P, capacity,
+                            a->frame_seq, a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr, stream);
   }
   GAB_STAGE_CHECK(f.dbg, stream);
   GAB_CUDA(cudaMemcpyAsync(f.ctr_host, g.buckets.meta, sizeof(uint32_t) * GAB200_NUM_COUNTERS, cudaMemcpyDeviceToHost,
@@ -391,7 +408,7 @@ int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capaci
 // emit -> per-instance tile sort -> ranges -> tile order -> blend, for a binning buffer of `cap` instances.
 // n_known >= 0: exactly that many instances exist (no padding); n_known < 0: the count is only on the device -- the
 // tile sort runs over the whole capacity, unused slots carry the sentinel key and sort behind every tile.
-int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, size_t sort_temp) {
+int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, size_t sort_temp, bool redo) {
   const gab200_forward_args* a = f.a;
   gab200_frame_state* st = f.st;
   cudaStream_t stream = f.stream;
@@ -401,35 +418,59 @@ int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, siz
   st->binning_buffer = bin;
   st->binning_bytes = bv.bytes;
   const int64_t n_sort = n_known >= 0 ? n_known : cap;
-  GAB_CUDA(cudaMemsetAsync(f.iv.ranges, 0, sizeof(uint2) * ((size_t)tiles + 1), stream));
+  const bool counting = f.counting && f.P > 0;
+  st->tile_sort_path = counting ? 0 : 1;
   if (bv.strip_mask != nullptr && n_sort > 0) GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)n_sort, stream));
   int selector = 0;
-  if (n_sort > 0) {
-    if (n_known < 0) GAB_CUDA(cudaMemsetAsync(bv.keys[0], 0xff, sizeof(uint32_t) * (size_t)cap, stream));
-    {
-      StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
-      launch_emit_keys(f.P, f.gx, f.gy, f.g.rec, f.g.aux, f.g.ids[f.selA], f.g.offsets, f.order_count, f.g.buckets.meta,
-                       (uint32_t)cap, bv.keys[0], bv.vals[0], a->exact_binning, stream);
-    }
-    GAB_STAGE_CHECK(f.dbg, stream);
-    {
-      StageScope sc(GAB200_STAGE_SORT, stream);
-      GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], n_sort,
-                        st->sort_bits, &selector, stream));
-    }
-    GAB_STAGE_CHECK(f.dbg, stream);
-    {
+  if (counting) {
+    if (redo) {  // the cursors were consumed (and the ranges possibly cut at a smaller capacity) by the first attempt
       StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-      launch_tile_ranges(n_sort, (uint32_t)tiles, bv.keys[selector], f.iv.ranges, stream);
+      f.scan_clamp = (uint32_t)(cap < 0xffffffffll ? cap : 0xffffffffll);
+      launch_tile_scan_order(tiles, f.iv.tile_count, f.scan_clamp, f.iv.ranges, f.iv.tile_cursor, f.iv.order,
+                             f.iv.order_info, f.g.buckets.meta, tune_get(GAB200_TUNE_HEAVY_FWD),
+                             tune_get(GAB200_TUNE_HEAVY_BWD), stream);
     }
-    GAB_STAGE_CHECK(f.dbg, stream);
+    if (n_sort > 0) {
+      {
+        StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
+        launch_emit_keys(f.P, f.gx, f.gy, f.g.rec, f.g.aux, f.g.ids[f.selA], nullptr, f.order_count, f.g.buckets.meta,
+                         (uint32_t)cap, f.iv.tile_cursor, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+      }
+      GAB_STAGE_CHECK(f.dbg, stream);
+      {
+        StageScope sc(GAB200_STAGE_SORT, stream);
+        launch_tile_sort(tiles, f.iv.ranges, f.iv.order, f.iv.order_info, bv.keys[0], bv.vals[0], f.g.ids[f.selA],
+                         f.order_count, f.P, stream);
+      }
+      GAB_STAGE_CHECK(f.dbg, stream);
+    }
+  } else {
+    GAB_CUDA(cudaMemsetAsync(f.iv.ranges, 0, sizeof(uint2) * ((size_t)tiles + 1), stream));
+    if (n_sort > 0) {
+      if (n_known < 0) GAB_CUDA(cudaMemsetAsync(bv.keys[0], 0xff, sizeof(uint32_t) * (size_t)cap, stream));
+      {
+        StageScope sc(GAB200_STAGE_EMIT_KEYS, stream);
+        launch_emit_keys(f.P, f.gx, f.gy, f.g.rec, f.g.aux, f.g.ids[f.selA], f.g.offsets, f.order_count, f.g.buckets.meta,
+                         (uint32_t)cap, nullptr, bv.keys[0], bv.vals[0], a->exact_binning, stream);
+      }
+      GAB_STAGE_CHECK(f.dbg, stream);
+      {
+        StageScope sc(GAB200_STAGE_SORT, stream);
+        GAB_CUDA(run_sort(bv.sort_temp, bv.sort_temp_bytes, bv.keys[0], bv.keys[1], bv.vals[0], bv.vals[1], n_sort,
+                          st->sort_bits, &selector, stream));
+      }
+      GAB_STAGE_CHECK(f.dbg, stream);
+      {
+        StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+        launch_tile_ranges(n_sort, (uint32_t)tiles, bv.keys[selector], f.iv.ranges, stream);
+      }
+      GAB_STAGE_CHECK(f.dbg, stream);
+    }
+    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
+    launch_tile_scan_order(tiles, nullptr, 0xffffffffu, f.iv.ranges, nullptr, f.iv.order, f.iv.order_info, nullptr,
+                           tune_get(GAB200_TUNE_HEAVY_FWD), tune_get(GAB200_TUNE_HEAVY_BWD), stream);
   }
   st->sorted_selector = selector;
-  {
-    StageScope sc(GAB200_STAGE_TILE_RANGES, stream);
-    launch_tile_order(tiles, f.iv.ranges, f.iv.order, f.iv.order_info, tune_get(GAB200_TUNE_HEAVY_FWD),
-                      tune_get(GAB200_TUNE_HEAVY_BWD), stream);
-  }
   {
     StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
     launch_blend_forward(f.W, f.H, f.iv.ranges, f.iv.order, f.iv.order_info, bv.vals[selector], f.g.rec, a->bg,
@@ -459,6 +500,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   f.gx = (f.W + GAB_TILE - 1) / GAB_TILE; f.gy = (f.H + GAB_TILE - 1) / GAB_TILE;
   f.nb = a->need_backward != 0;
   f.dbg = a->debug != 0;
+  f.counting = tune_get(GAB200_TUNE_TILE_SORT) == 0;
   const int P = f.P;
   const int mode = a->sync_mode;
   const bool speculative = mode != GAB200_SYNC_EXACT;  // binning + blend are enqueued before N is known
@@ -497,7 +539,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     void* bin = a->alloc_binning(a->alloc_user, bsz.bytes);
     if (bin == nullptr) return GAB200_ERR_ALLOC;
     GAB_CUDA(cudaMemsetAsync(f.g.buckets.counts, 0, f.g.bucket_clear_bytes, stream));
-    const int rc = enqueue_binning_blend(f, bin, 0, 0, 0);
+    const int rc = enqueue_binning_blend(f, bin, 0, 0, 0, false);
     if (rc < 0) return rc;
     st->num_rendered = st->num_candidates = 0;
     return 0;
@@ -523,7 +565,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   host_add(0, t_alloc - t0);
   if (a->binning_hint > 0) {
     bin_cap = a->binning_hint;
-    tempB = cached_sort_temp_bytes(bin_cap, st->sort_bits);
+    tempB = f.counting ? 0 : cached_sort_temp_bytes(bin_cap, st->sort_bits);
     const BinView hv = carve_binning(nullptr, bin_cap, f.nb, tempB);
     bin = a->alloc_binning(a->alloc_user, hv.bytes);
     if (bin == nullptr) return GAB200_ERR_ALLOC;
@@ -531,7 +573,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   double t1 = now_us();
   host_add(2, t1 - t_alloc);
   if (speculative) {
-    rc = enqueue_binning_blend(f, bin, cap, -1, tempB);
+    rc = enqueue_binning_blend(f, bin, cap, -1, tempB, false);
     if (rc < 0) return rc;
     const double t2 = now_us();
     host_add(3, t2 - t1);
@@ -572,14 +614,14 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   if (redo) {
     if (bin == nullptr || N > bin_cap) {  // exact size: the layout depends on the capacity
       bin_cap = N;
-      tempB = cached_sort_temp_bytes(bin_cap > 0 ? bin_cap : 1, st->sort_bits);
+      tempB = f.counting ? 0 : cached_sort_temp_bytes(bin_cap > 0 ? bin_cap : 1, st->sort_bits);
       const BinView bsz = carve_binning(nullptr, bin_cap, f.nb, tempB);
       bin = a->alloc_binning(a->alloc_user, bsz.bytes);
       if (bin == nullptr) return GAB200_ERR_ALLOC;
     }
     const double t3 = now_us();
     host_add(2, t3 - t2);
-    rc = enqueue_binning_blend(f, bin, bin_cap, N, tempB);
+    rc = enqueue_binning_blend(f, bin, bin_cap, N, tempB, speculative);
     if (rc < 0) return rc;
     host_add(3, now_us() - t3);
   }
@@ -737,7 +779,10 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
   const size_t N = (size_t)st->num_rendered;
   if (keys && N) {
     GeomView g = carve_geom(st->geom_buffer, a->P, a->need_backward != 0, 0);
-    launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], bv.vals[st->sorted_selector], g.aux, keys, stream);
+    if (st->tile_sort_path == 0)  // counting tile sort: the instance arrays hold (rank, id); the tile is in the ranges
+      launch_expand_keys_by_range(gx * gy, iv.ranges, bv.vals[0], g.aux, keys, stream);
+    else
+      launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], bv.vals[st->sorted_selector], g.aux, keys, stream);
   }
   if (values && N) GAB_CUDA(cudaMemcpyAsync(values, bv.vals[st->sorted_selector], 4 * N, cudaMemcpyDeviceToDevice, stream));
   if (ranges) GAB_CUDA(cudaMemcpyAsync(ranges, iv.ranges, sizeof(uint2) * (size_t)gx * gy, cudaMemcpyDeviceToDevice, stream));

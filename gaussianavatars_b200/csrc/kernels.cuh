@@ -93,9 +93,10 @@ __device__ __forceinline__ uint32_t depth_bucket(uint32_t key, const DepthBucket
   const uint32_t b = (uint32_t)(__uint2float_rz(key - d.lo) * d.scale);
   return b < d.nb ? b : d.nb - 1u;
 }
+// tile_count != nullptr: also count the instances of every tile (counting tile sort, tile_sort.cu)
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
                        uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, const DepthBuckets& buckets,
-                       cudaStream_t stream);
+                       uint32_t* tile_count, cudaStream_t stream);
 // depth_keys [P] (by splat) -> sorted_ids [M] in (key, id) order and offsets [M] = inclusive instance counts
 void launch_depth_bucket_sort(int P, const DepthBuckets& buckets, const uint32_t* depth_keys,
                               const uint32_t* tiles_touched, uint32_t* scratch_keys, uint32_t* sorted_ids,
@@ -103,20 +104,31 @@ void launch_depth_bucket_sort(int P, const DepthBuckets& buckets, const uint32_t
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);
-// counters[NUM_RENDERED / NUM_LISTED] of a radix-sorted frame (offsets != nullptr), capacity and sequence number
+// counters[NUM_LISTED] (+ NUM_RENDERED from offsets when given) of a radix-sorted frame (P > 0; pass 0 for a
+// bucket-sorted one, whose kernels wrote them), capacity and sequence number
 void launch_publish_counters(uint32_t* counters, const uint32_t* offsets, int P, uint32_t capacity, uint32_t seq,
                              uint32_t* sticky_overflow, cudaStream_t stream);
 // `capacity`: instances the key/value arrays hold -- anything beyond is dropped (the frame's counters say so);
 // counters[BUCKET_OVERFLOW] != 0 (depth order unusable) emits nothing.
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
                       const uint32_t* offsets, const uint32_t* order_count, const uint32_t* counters, uint32_t capacity,
-                      uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
+                      uint32_t* cursor, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream);
 // keys[0..N) sorted; entries with key >= tiles are padding (sentinel) behind the last real instance
 void launch_tile_ranges(int64_t N, uint32_t tiles, const uint32_t* keys, uint2* ranges, cudaStream_t stream);
 void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
                         cudaStream_t stream);
-void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, int heavy_fwd,
-                       int heavy_bwd, cudaStream_t stream);
+// tile_sort.cu
+#define GAB_TILE_SORT_SMEM 2048  // entries one CTA sorts in shared memory; longer tile lists take the bitmap kernel
+// tile_count != nullptr: ranges / cursors / counters[NUM_RENDERED] from the per-tile counts (ranges cut at `clamp`);
+// always: heaviest-first tile order + heavy/light split points (order_info[0..1]) + number of long tiles ([2])
+void launch_tile_scan_order(int tiles, const uint32_t* tile_count, uint32_t clamp, uint2* ranges, uint32_t* cursor,
+                            uint32_t* order, uint32_t* order_info, uint32_t* counters, int heavy_fwd, int heavy_bwd,
+                            cudaStream_t stream);
+// every tile's (rank, id) segment sorted by rank; ids written back in place
+void launch_tile_sort(int tiles, const uint2* ranges, const uint32_t* order, const uint32_t* order_info, uint32_t* keys,
+                      uint32_t* vals, const uint32_t* rank_to_id, const uint32_t* listed, int P, cudaStream_t stream);
+void launch_expand_keys_by_range(int tiles, const uint2* ranges, const uint32_t* ids, const SplatAux* aux, uint64_t* out,
+                                 cudaStream_t stream);
 
 // binning.cu (cub)
 size_t scan_temp_bytes(int P);

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
                                                             uint8_t* __restrict__ clamped,
                                                             uint32_t* __restrict__ depth_keys,
                                                             uint32_t* __restrict__ ids, int exact_binning,
-                                                            DepthBuckets bk) {
+                                                            DepthBuckets bk, uint32_t* __restrict__ tile_count) {
   __shared__ Camera cam;
   __shared__ float sh_s[PRE_NT * SH_SMEM_STRIDE_MAX];
   stage_camera(a, cam);
@@ -186,8 +186,13 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
                       (conic_z * REC_SCALE_AC) / REC_SCALE_AC, opacity, x0, x1);
         const float ext_x = !span.any ? -1.f : (span.full ? 1.0e30f : span.dxmax + 0.02f);
         const float ext_y = !span.any ? -1.f : (span.full ? 1.0e30f : span.ymax + 0.02f);
+        // instance count of the splat; with `tile_count` (counting tile sort, tile_sort.cu) also one RED per instance
+        // into its tile's counter, so that the tile ranges exist before anything is emitted
         if (exact_binning) {
           tiles_out = (uint32_t)((y1 - y0) * (x1 - x0));
+          if (tile_count != nullptr)
+            for (int ty = y0; ty < y1; ty++)
+              for (int x = x0; x < x1; x++) atomicAdd(tile_count + ty * gx + x, 1u);
         } else {
           uint32_t cnt = 0;
           if (span.any)
@@ -195,6 +200,8 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
               int cx0, cx1;
               span.row(ty, cx0, cx1);
               cnt += (uint32_t)(cx1 - cx0);
+              if (tile_count != nullptr)
+                for (int x = cx0; x < cx1; x++) atomicAdd(tile_count + ty * gx + x, 1u);
             }
           tiles_out = cnt;
         }
@@ -234,13 +241,15 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
 
 void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* aux, uint32_t* tiles_touched,
                        uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, const DepthBuckets& buckets,
-                       cudaStream_t stream) {
+                       uint32_t* tile_count, cudaStream_t stream) {
   const int threads = PRE_NT, blocks = (a.P + threads - 1) / threads;
   if (blocks == 0) return;
   if (a.input_mode == GAB200_INPUT_BOUND_RAW)
-    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning, buckets);
+    preprocess_kernel<true><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids,
+                                                            a.exact_binning, buckets, tile_count);
   else
-    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids, a.exact_binning, buckets);
+    preprocess_kernel<false><<<blocks, threads, 0, stream>>>(a, rec, aux, tiles_touched, clamped, depth_keys, ids,
+                                                             a.exact_binning, buckets, tile_count);
   count_launch();
 }
 
@@ -459,9 +468,23 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
                                                         const uint32_t* __restrict__ offsets,
                                                         const uint32_t* __restrict__ order_count,
                                                         const uint32_t* __restrict__ counters, uint32_t cap,
+                                                        uint32_t* __restrict__ cursor,
                                                         uint32_t* __restrict__ keys, uint32_t* __restrict__ vals,
                                                         int exact_binning) {
   constexpr unsigned FULL = 0xffffffffu;
+  // cursor != nullptr (counting tile sort): an instance goes to the next free slot of ITS TILE's segment and carries
+  // the splat's depth rank as key; otherwise it goes to offsets[...] + k in emission order with the tile id as key
+  // (input of the stable radix sort by tile).
+  auto put = [&](uint32_t o, uint32_t tile, uint32_t rank, uint32_t id) {
+    if (cursor != nullptr) {
+      o = atomicAdd(cursor + tile, 1u);
+      tile = rank;
+    }
+    if (o < cap) {
+      keys[o] = tile;
+      vals[o] = id;
+    }
+  };
   // a depth bucket overflowed: `order` / `offsets` are incomplete, the host (or the graph's owner) redoes the frame
   if (order_count != nullptr && counters[GAB200_CTR_BUCKET_OVERFLOW] != 0) return;
   const int lane = threadIdx.x & 31;
@@ -482,7 +505,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       px = q0.x; py = q0.y; op = q1.y;
       cA = q0.z / REC_SCALE_AC; cB = q0.w / REC_SCALE_B; cC = q1.x / REC_SCALE_AC;  // undo the blend pre-scale
       radius = ax.radius;
-      off = (slot == 0) ? 0u : offsets[slot - 1];
+      off = (slot == 0 || offsets == nullptr) ? 0u : offsets[slot - 1];
     }
   }
   int x0 = 0, y0 = 0, x1 = 0, y1 = 0;
@@ -500,10 +523,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const uint32_t sid = __shfl_sync(FULL, i, src);
       for (int t = lane; t < cnt; t += 32) {
         const int y = sy0 + t / w, x = sx0 + t % w;
-        if (soff + t < cap) {
-          keys[soff + t] = (uint32_t)(y * gx + x);
-          vals[soff + t] = sid;
-        }
+        put(soff + t, (uint32_t)(y * gx + x), (uint32_t)(warp_global * 32 + src), sid);
       }
     }
     return;
@@ -518,10 +538,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       int cx0, cx1;
       span.row(ty, cx0, cx1);
       for (int x = cx0; x < cx1; x++) {
-        if (o < cap) {
-          keys[o] = (uint32_t)(ty * gx + x);
-          vals[o] = i;
-        }
+        put(o, (uint32_t)(ty * gx + x), (uint32_t)slot, i);
         o++;
       }
     }
@@ -551,10 +568,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       }
       uint32_t o = base + (uint32_t)(incl - len);
       for (int x = cx0; x < cx1; x++) {
-        if (o < cap) {
-          keys[o] = (uint32_t)(ty * gx + x);
-          vals[o] = sid;
-        }
+        put(o, (uint32_t)(ty * gx + x), (uint32_t)(warp_global * 32 + src), sid);
         o++;
       }
       base += (uint32_t)__shfl_sync(FULL, incl, 31);
@@ -564,8 +578,8 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
 
 __global__ void publish_counters_kernel(uint32_t* __restrict__ counters, const uint32_t* __restrict__ offsets, int P,
                                         uint32_t capacity, uint32_t seq, uint32_t* __restrict__ sticky_overflow) {
-  if (offsets != nullptr) {  // radix-sorted frame: every splat is listed, N is the last inclusive offset
-    counters[GAB200_CTR_NUM_RENDERED] = offsets[P - 1];
+  if (P > 0) {  // radix-sorted frame: every splat is listed; N is the last inclusive offset (unless already counted)
+    if (offsets != nullptr) counters[GAB200_CTR_NUM_RENDERED] = offsets[P - 1];
     counters[GAB200_CTR_NUM_LISTED] = (uint32_t)P;
     counters[GAB200_CTR_BUCKET_OVERFLOW] = 0;
   }
@@ -583,12 +597,12 @@ void launch_publish_counters(uint32_t* counters, const uint32_t* offsets, int P,
 
 void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux* aux, const uint32_t* order,
                       const uint32_t* offsets, const uint32_t* order_count, const uint32_t* counters, uint32_t cap,
-                      uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
+                      uint32_t* cursor, uint32_t* keys, uint32_t* vals, int exact_binning, cudaStream_t stream) {
   const int warps = (P + 31) / 32;
   const int threads = 256, blocks = (warps * 32 + threads - 1) / threads;
   if (blocks == 0) return;
-  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, order_count, counters, cap, keys,
-                                                   vals, exact_binning);
+  emit_keys_kernel<<<blocks, threads, 0, stream>>>(P, gx, gy, rec, aux, order, offsets, order_count, counters, cap, cursor,
+                                                   keys, vals, exact_binning);
   count_launch();
 }
 
@@ -612,67 +626,6 @@ __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, uint32_t ti
     }
   }
   if (idx == N - 1) ranges[cur].y = (uint32_t)N;
-}
-
-// Heaviest-first launch order of the tiles (longest-processing-time-first): the blend kernels walk one tile per
-// CTA and a tile's cost is proportional to its list length, so dispatching long lists first removes the tail where
-// a few SMs grind through 2000-deep lists while the rest idle.  Single CTA, counting sort into 64 length buckets.
-#define ORDER_NB 64
-#define ORDER_WARPS 32
-__global__ void __launch_bounds__(32 * ORDER_WARPS) tile_order_kernel(int tiles, const uint2* __restrict__ ranges,
-                                                                      uint32_t* __restrict__ order,
-                                                                      uint32_t* __restrict__ order_info, int heavy_fwd,
-                                                                      int heavy_bwd) {
-  // counting sort by list-length bucket (descending).  Every warp owns a private histogram / cursor row, so shared
-  // atomics only collide inside a warp (most tiles share a few buckets, e.g. "empty": a single row would serialise
-  // the whole CTA); the order inside a bucket is irrelevant.
-  __shared__ uint32_t hist[ORDER_WARPS][ORDER_NB + 1];
-  __shared__ uint32_t bucket_base[ORDER_NB];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int k = threadIdx.x; k < ORDER_WARPS * (ORDER_NB + 1); k += blockDim.x) (&hist[0][0])[k] = 0;
-  __syncthreads();
-  auto bucket = [](uint2 r) -> int {
-    const uint32_t len = r.y - r.x;
-    return len == 0 ? ORDER_NB - 1 : (ORDER_NB - 2) - (int)min((uint32_t)(ORDER_NB - 2), len >> 5);
-  };
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) atomicAdd(&hist[warp][bucket(ranges[t])], 1u);
-  __syncthreads();
-  // bucket totals and per-warp starting offsets: thread b < ORDER_NB walks the warps of bucket b
-  if (threadIdx.x < ORDER_NB) {
-    uint32_t run = 0;
-    for (int w = 0; w < ORDER_WARPS; w++) {
-      const uint32_t c = hist[w][threadIdx.x];
-      hist[w][threadIdx.x] = run;  // exclusive offset of warp w inside the bucket
-      run += c;
-    }
-    bucket_base[threadIdx.x] = run;  // total
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    uint32_t run = 0;
-    // a tile is "heavy" for a pass when its list has >= heavy_* splats (multiples of 32): prefix of the order
-    const int qf = min(ORDER_NB - 2, max(1, heavy_fwd >> 5)), qb = min(ORDER_NB - 2, max(1, heavy_bwd >> 5));
-    for (int b = 0; b < ORDER_NB; b++) {
-      const uint32_t c = bucket_base[b];
-      bucket_base[b] = run;
-      run += c;
-      if (b == (ORDER_NB - 2) - qf) order_info[0] = run;
-      if (b == (ORDER_NB - 2) - qb) order_info[1] = run;
-    }
-  }
-  __syncthreads();
-  (void)lane;
-  for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
-    const int b = bucket(ranges[t]);
-    order[bucket_base[b] + atomicAdd(&hist[warp][b], 1u)] = (uint32_t)t;
-  }
-}
-
-void launch_tile_order(int tiles, const uint2* ranges, uint32_t* order, uint32_t* order_info, int heavy_fwd,
-                       int heavy_bwd, cudaStream_t stream) {
-  if (tiles == 0) return;
-  tile_order_kernel<<<1, 1024, 0, stream>>>(tiles, ranges, order, order_info, heavy_fwd, heavy_bwd);
-  count_launch();
 }
 
 __global__ void expand_keys_kernel(int64_t N, const uint32_t* __restrict__ tile_keys, const uint32_t* __restrict__ ids,

@@ -177,6 +177,8 @@ typedef struct gab200_frame_state {
   uint32_t depth_key_max;
   int32_t depth_sort_path;    /* 0: radix sort (no hint); 1: bucket sort; 2: bucket sort overflowed, radix sort redone */
   int32_t attempts;           /* 1 + number of times stages were re-enqueued (GAB200_SYNC_LATE only; else 1) */
+  int32_t tile_sort_path;     /* 0: counting sort by tile + per-tile rank sort; 1: cub::DeviceRadixSort over the instances */
+  int32_t reserved0;
   const uint32_t* device_counters; /* GAB200_NUM_COUNTERS words inside the geometry buffer (valid as long as it is) */
 } gab200_frame_state;
 
@@ -343,6 +345,9 @@ enum {
                                   for 5 CTAs per SM; 6 = 1 with specialised bodies; 7 = 2 for 6 CTAs per SM.
                                   Measured at the headline size (profiles/r02/bwd_variants.jsonl): 211 / 198 / 179 /
                                   175 / 182 / 185 / 186 / 211 us */
+  GAB200_TUNE_TILE_SORT = 4,   /* per-instance sort by tile: 0 (default) counting sort + per-tile rank sort (2-3 launches,
+                                  csrc/tile_sort.cu); 1 cub::DeviceRadixSort::SortPairs over the instances (5 launches +
+                                  tile-range detection).  Identical sorted streams. */
   GAB200_NUM_TUNABLES = 8
 };
 int32_t gab200_tune(int32_t knob, int32_t value);

@@ -11,6 +11,15 @@ from tests.test_gpu_parity import _run_cuda, _dev
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["counting-tile-sort", "cub-radix-tile-sort"])
+def tile_sort_implementation(request):
+    from gaussianavatars_b200 import _native as N
+
+    N.tune(N.TUNE_TILE_SORT, 0 if request.param.startswith("counting") else 1)
+    yield
+    N.tune(N.TUNE_TILE_SORT, 0)
+
+
 def _stream(scene, dev, hint=None, exact=True):
     """One forward; returns (image, radii, keys, vals, ranges, n, depth_sort_path)."""
     from gaussianavatars_b200 import rasterizer as R

@@ -8,6 +8,17 @@ from tests import helpers as h
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["counting-tile-sort", "cub-radix-tile-sort"])
+def tile_sort_implementation(request):
+    """Every test of this file runs on both implementations of the per-instance sort by tile
+    (include/gab200_rasterizer.h GAB200_TUNE_TILE_SORT): the sorted stream, image and gradients must not depend on it."""
+    from gaussianavatars_b200 import _native as N
+
+    N.tune(N.TUNE_TILE_SORT, 0 if request.param.startswith("counting") else 1)
+    yield
+    N.tune(N.TUNE_TILE_SORT, 0)
+
+
 def _dev():
     return torch.device("cuda:0")
 
@@ -47,6 +58,25 @@ def test_forward_and_sorted_keys_bit_exact(P, W, H, deg, seed):
     assert np.array_equal(vals.cpu().numpy().view(np.uint32), st.vals_sorted), "sorted splat ids not bit-exact"
     assert np.array_equal(ranges.cpu().numpy().view(np.uint32), st.ranges), "tile ranges differ"
     h.assert_image_close(img.cpu().numpy(), st.out_color, "forward image")
+
+
+def test_long_tile_lists_take_the_bitmap_sort_and_stay_bit_exact():
+    """Every splat covers every tile: 5,000-entry lists, beyond the 2048 entries a CTA sorts in shared memory
+    (tile_sort_long_kernel).  Sorted stream still bit-identical to the oracle's."""
+    from gaussianavatars_b200 import rasterizer as R
+
+    dev = _dev()
+    scene = h.random_scene(5_000, 64, 48, sh_degree=0, seed=21, scale_shift=2.5)
+    st = h.oracle_forward(scene)
+    lens = st.ranges[:, 1].astype(np.int64) - st.ranges[:, 0]
+    assert lens.max() > 2048, f"scene only reaches {lens.max()} entries per tile"
+    img, radii, _, _ = _run_cuda(scene, dev, exact=True)
+    keys, vals, ranges, n = R.export_last_binning()
+    assert n == st.N
+    assert np.array_equal(keys.cpu().numpy().view(np.uint64), st.keys_sorted)
+    assert np.array_equal(vals.cpu().numpy().view(np.uint32), st.vals_sorted)
+    assert np.array_equal(ranges.cpu().numpy().view(np.uint32), st.ranges)
+    h.assert_image_close(img.cpu().numpy(), st.out_color, "long-list image")
 
 
 def test_culled_binning_is_exact_subsequence_and_same_image():
