@@ -88,6 +88,44 @@ class AdamSegment(C.Structure):
     ]
 
 
+class DensifyArgs(C.Structure):
+    """Mirror of gab200_densify_args."""
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("P", C.c_int32), ("num_faces", C.c_int32), ("sh_rest_width", C.c_int32),
+        ("grad_threshold", C.c_float), ("min_opacity", C.c_float), ("extent", C.c_float), ("percent_dense", C.c_float),
+        ("max_screen_size", C.c_float),
+        ("xyz", C.c_void_p), ("rotation", C.c_void_p), ("scaling", C.c_void_p), ("opacity", C.c_void_p),
+        ("f_dc", C.c_void_p), ("f_rest", C.c_void_p),
+        ("exp_avg", C.c_void_p * 6), ("exp_avg_sq", C.c_void_p * 6),
+        ("xyz_gradient_accum", C.c_void_p), ("denom", C.c_void_p),
+        ("binding", C.c_void_p), ("binding_counter", C.c_void_p), ("face_scaling", C.c_void_p),
+        ("scratch", C.c_void_p), ("totals_host", C.c_void_p),
+    ]
+
+
+class DensifyOut(C.Structure):
+    """Mirror of gab200_densify_out."""
+    _fields_ = [
+        ("P_out", C.c_int32), ("n_child_rows", C.c_int32),
+        ("xyz", C.c_void_p), ("rotation", C.c_void_p), ("scaling", C.c_void_p), ("opacity", C.c_void_p),
+        ("f_dc", C.c_void_p), ("f_rest", C.c_void_p),
+        ("exp_avg", C.c_void_p * 6), ("exp_avg_sq", C.c_void_p * 6),
+        ("binding", C.c_void_p), ("binding_counter", C.c_void_p), ("noise", C.c_void_p),
+        ("src_scratch", C.c_void_p), ("kind_scratch", C.c_void_p), ("noise_row_scratch", C.c_void_p),
+    ]
+
+
+class RegularizeArgs(C.Structure):
+    """Mirror of gab200_regularize_args."""
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("P", C.c_int32), ("metric_xyz", C.c_int32), ("metric_scale", C.c_int32),
+        ("threshold_xyz", C.c_float), ("threshold_scale", C.c_float), ("lambda_xyz", C.c_float), ("lambda_scale", C.c_float),
+        ("xyz", C.c_void_p), ("scaling", C.c_void_p), ("radii", C.c_void_p), ("binding", C.c_void_p),
+        ("face_scaling", C.c_void_p), ("loss", C.c_void_p), ("sums", C.c_void_p),
+        ("grad_xyz", C.c_void_p), ("grad_scaling", C.c_void_p), ("grad_face_scaling", C.c_void_p),
+    ]
+
+
 ADAM_MAX_SEGMENTS = 8
 PHOTOMETRIC_SCRATCH_HEAD = 4
 
@@ -95,7 +133,8 @@ EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", 
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
                     "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8",
-                    "gab200_photometric_loss", "gab200_adam_step", "gab200_tune", "gab200_counters_ok")
+                    "gab200_photometric_loss", "gab200_adam_step", "gab200_tune", "gab200_counters_ok",
+                    "gab200_regularize_forward", "gab200_regularize_backward", "gab200_densify_scratch_bytes", "gab200_densify_plan", "gab200_densify_apply")
 
 _lib = None
 _lock = threading.Lock()
@@ -139,6 +178,16 @@ def lib():
         L.gab200_launch_count.restype = C.c_int64
         L.gab200_tune.restype = C.c_int32
         L.gab200_tune.argtypes = [C.c_int32, C.c_int32]
+        L.gab200_regularize_forward.restype = C.c_int32
+        L.gab200_regularize_forward.argtypes = [C.POINTER(RegularizeArgs), C.c_void_p]
+        L.gab200_regularize_backward.restype = C.c_int32
+        L.gab200_regularize_backward.argtypes = [C.POINTER(RegularizeArgs), C.c_void_p, C.c_void_p]
+        L.gab200_densify_scratch_bytes.restype = C.c_size_t
+        L.gab200_densify_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
+        L.gab200_densify_plan.restype = C.c_int32
+        L.gab200_densify_plan.argtypes = [C.POINTER(DensifyArgs), C.c_void_p]
+        L.gab200_densify_apply.restype = C.c_int32
+        L.gab200_densify_apply.argtypes = [C.POINTER(DensifyArgs), C.POINTER(DensifyOut), C.c_void_p]
         L.gab200_counters_ok.restype = C.c_int32
         L.gab200_counters_ok.argtypes = [C.c_void_p, C.c_uint32]
         L.gab200_l1_loss_u8.restype = C.c_int32

@@ -25,6 +25,8 @@ SOURCES = {
     "preprocess_bwd.cu": [],
     "binning.cu": [],
     "tile_sort.cu": [],
+    "densify.cu": [],
+    "regularize.cu": [],
     "blend.cu": [],
     "face_frame.cu": [],
     "loss.cu": [],

@@ -419,7 +419,7 @@ int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, siz
   st->binning_bytes = bv.bytes;
   const int64_t n_sort = n_known >= 0 ? n_known : cap;
   const bool counting = f.counting && f.P > 0;
-  st->tile_sort_path = counting ? 0 : 1;
+  st->tile_sort_path = counting ? 1 : 0;
   if (bv.strip_mask != nullptr && n_sort > 0) GAB_CUDA(cudaMemsetAsync(bv.strip_mask, 0, (size_t)n_sort, stream));
   int selector = 0;
   if (counting) {
@@ -500,7 +500,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
   f.gx = (f.W + GAB_TILE - 1) / GAB_TILE; f.gy = (f.H + GAB_TILE - 1) / GAB_TILE;
   f.nb = a->need_backward != 0;
   f.dbg = a->debug != 0;
-  f.counting = tune_get(GAB200_TUNE_TILE_SORT) == 0;
+  f.counting = tune_get(GAB200_TUNE_TILE_SORT) == 1;
   const int P = f.P;
   const int mode = a->sync_mode;
   const bool speculative = mode != GAB200_SYNC_EXACT;  // binning + blend are enqueued before N is known
@@ -766,6 +766,64 @@ int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segs, 
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 
+static bool regularize_args_ok(const gab200_regularize_args* a, bool backward) {
+  if (a == nullptr || a->abi_version != GAB200_ABI_VERSION || a->P < 0 || !a->loss || !a->sums) return false;
+  if (a->P > 0 && (!a->xyz || !a->scaling || !a->radii)) return false;
+  if ((a->metric_xyz || a->metric_scale) && a->binding != nullptr && !a->face_scaling) return false;
+  if (backward && a->P > 0 && (!a->grad_xyz || !a->grad_scaling)) return false;
+  return true;
+}
+int32_t gab200_regularize_forward(const gab200_regularize_args* a, void* stream_) {
+  if (!regularize_args_ok(a, false)) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(launch_regularize_forward(*a, (cudaStream_t)stream_));
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+int32_t gab200_regularize_backward(const gab200_regularize_args* a, const float* g_out, void* stream_) {
+  if (!regularize_args_ok(a, true) || g_out == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(launch_regularize_backward(*a, g_out, (cudaStream_t)stream_));
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+size_t gab200_densify_scratch_bytes(int32_t P, int32_t F) { return densify_scratch_bytes(P < 0 ? 0 : P, F < 0 ? 0 : F); }
+
+static bool densify_args_ok(const gab200_densify_args* a) {
+  if (a == nullptr || a->abi_version != GAB200_ABI_VERSION || a->P < 0 || a->sh_rest_width < 0) return false;
+  if (a->scratch == nullptr || a->totals_host == nullptr) return false;
+  if (a->P > 0 && (!a->xyz || !a->rotation || !a->scaling || !a->opacity || !a->f_dc || !a->xyz_gradient_accum || !a->denom))
+    return false;
+  if (a->P > 0 && a->sh_rest_width > 0 && !a->f_rest) return false;
+  if (a->binding != nullptr && (a->num_faces <= 0 || !a->binding_counter || !a->face_scaling)) return false;
+  return true;
+}
+
+int32_t gab200_densify_plan(const gab200_densify_args* a, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!densify_args_ok(a)) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(launch_densify_plan(*a, stream));
+  GAB_CUDA(cudaStreamSynchronize(stream));  // the caller sizes the outputs from totals_host
+  const uint64_t rows = (uint64_t)a->totals_host[0] + a->totals_host[1] + 2ull * a->totals_host[2];
+  if (rows > 0x7fffffffull) return GAB200_ERR_OVERFLOW;
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_densify_apply(const gab200_densify_args* a, const gab200_densify_out* o, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!densify_args_ok(a) || o == nullptr || o->P_out < 0 || o->n_child_rows < 0) return GAB200_ERR_INVALID_ARGUMENT;
+  if (o->P_out > 0) {
+    if (!o->xyz || !o->rotation || !o->scaling || !o->opacity || !o->f_dc || !o->src_scratch || !o->kind_scratch)
+      return GAB200_ERR_INVALID_ARGUMENT;
+    if (a->sh_rest_width > 0 && !o->f_rest) return GAB200_ERR_INVALID_ARGUMENT;
+    if (o->n_child_rows > 0 && (!o->noise || !o->noise_row_scratch)) return GAB200_ERR_INVALID_ARGUMENT;
+    if (a->binding != nullptr && (!o->binding || !o->binding_counter)) return GAB200_ERR_INVALID_ARGUMENT;
+  }
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  GAB_CUDA(launch_densify_apply(*a, *o, stream));
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
 int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_state* st, uint64_t* keys,
                               uint32_t* values, uint32_t* ranges, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -779,7 +837,7 @@ int32_t gab200_export_binning(const gab200_forward_args* a, const gab200_frame_s
   const size_t N = (size_t)st->num_rendered;
   if (keys && N) {
     GeomView g = carve_geom(st->geom_buffer, a->P, a->need_backward != 0, 0);
-    if (st->tile_sort_path == 0)  // counting tile sort: the instance arrays hold (rank, id); the tile is in the ranges
+    if (st->tile_sort_path == 1)  // counting tile sort: the instance arrays hold (rank, id); the tile is in the ranges
       launch_expand_keys_by_range(gx * gy, iv.ranges, bv.vals[0], g.aux, keys, stream);
     else
       launch_expand_keys((int64_t)N, bv.keys[st->sorted_selector], bv.vals[st->sorted_selector], g.aux, keys, stream);

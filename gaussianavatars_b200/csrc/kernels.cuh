@@ -165,6 +165,15 @@ void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* gr
 void launch_photometric_loss(int C, int H, int W, const float* img, const void* gt, int gt_is_u8, float lambda,
                              float* grad, float* loss, float* scratch, cudaStream_t stream);
 
+// densify.cu
+size_t densify_scratch_bytes(int P, int F);
+cudaError_t launch_densify_plan(const gab200_densify_args& a, cudaStream_t stream);
+cudaError_t launch_densify_apply(const gab200_densify_args& a, const gab200_densify_out& o, cudaStream_t stream);
+
+// regularize.cu
+cudaError_t launch_regularize_forward(const gab200_regularize_args& a, cudaStream_t stream);
+cudaError_t launch_regularize_backward(const gab200_regularize_args& a, const float* g_out, cudaStream_t stream);
+
 // optim.cu
 void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, double beta1, double beta2, double eps,
                  cudaStream_t stream);

@@ -49,6 +49,10 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     __syncthreads();
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // the other 44 bytes per splat: positions / scales staged with 128-bit loads, quaternion as one float4
+  __shared__ float xyz_s[PRE_NT * 3], scale_s[PRE_NT * 3];
+  RawAttr raw;
+  load_raw_staged<PRE_NT>(a, i, xyz_s, scale_s, raw);
   if (i >= a.P) return;
   const float* my_sh = sh_s + threadIdx.x * sh_stride;
   const int W = a.image_width, H = a.image_height;
@@ -69,15 +73,16 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
   bool have_cov = false;
   if (BOUND) {
     Activated act;
-    bind_activate(a, i, act);
+    BindCtx bctx;
+    bind_activate(a, i, raw, act, bctx);
     p = act.mean;
     opacity = act.opacity;
     float s[3] = {a.scale_modifier * act.s[0], a.scale_modifier * act.s[1], a.scale_modifier * act.s[2]};
     cov3d_from_R(act.R, s, c3);
     have_cov = true;
   } else {
-    p = make_float3(a.means3D[3 * i], a.means3D[3 * i + 1], a.means3D[3 * i + 2]);
-    opacity = a.opacities[i];
+    p = make_float3(raw.x[0], raw.x[1], raw.x[2]);
+    opacity = raw.o;
   }
 
   const float3 t = xform4x3(cam.V, p);
@@ -94,9 +99,8 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
         for (int k = 0; k < 6; k++) c3[k] = a.cov3D_precomp[6 * (size_t)i + k];
       } else {
         float R[9];
-        quat_to_R(a.rotations[4 * i], a.rotations[4 * i + 1], a.rotations[4 * i + 2], a.rotations[4 * i + 3], R);
-        float s[3] = {a.scale_modifier * a.scales[3 * i], a.scale_modifier * a.scales[3 * i + 1],
-                      a.scale_modifier * a.scales[3 * i + 2]};
+        quat_to_R(raw.q[0], raw.q[1], raw.q[2], raw.q[3], R);
+        float s[3] = {a.scale_modifier * raw.s[0], a.scale_modifier * raw.s[1], a.scale_modifier * raw.s[2]};
         cov3d_from_R(R, s, c3);
       }
     }

@@ -144,20 +144,67 @@ struct BindCtx {
   int face;        // -1 when unbound
 };
 
-__device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, Activated& o, BindCtx& c) {
-  c.xl = make_float3(a.means3D[3 * (size_t)i], a.means3D[3 * (size_t)i + 1], a.means3D[3 * (size_t)i + 2]);
+// The 11 per-splat floats besides the SH coefficients (position, quaternion, scales, opacity; raw or activated
+// depending on the input mode).  The per-splat kernels fill it with 128-bit accesses: the quaternion is one float4
+// per thread, the two 12-byte-stride arrays (positions, scales) are staged through shared memory by stage_rows_in
+// (coalesced LDG.128, odd row stride), the 4-byte opacity is a coalesced scalar load.
+struct RawAttr {
+  float x[3], q[4], s[3], o;
+};
+// 16-byte aligned quaternion array -> one LDG.128 per splat
+__device__ __forceinline__ void load_quat(const float* __restrict__ rot, size_t i, float q[4]) {
+  if ((reinterpret_cast<uintptr_t>(rot) & 15) == 0) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(rot) + i);
+    q[0] = v.x; q[1] = v.y; q[2] = v.z; q[3] = v.w;
+  } else {
+    q[0] = rot[4 * i]; q[1] = rot[4 * i + 1]; q[2] = rot[4 * i + 2]; q[3] = rot[4 * i + 3];
+  }
+}
+// straight from global memory (kernels that do not stage: export, backward)
+__device__ __forceinline__ void load_raw(const gab200_forward_args& a, int i, RawAttr& r) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) r.x[k] = a.means3D[3 * (size_t)i + k];
+  if (a.rotations != nullptr) load_quat(a.rotations, (size_t)i, r.q);
+  if (a.scales != nullptr) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.s[k] = a.scales[3 * (size_t)i + k];
+  }
+  r.o = a.opacities[i];
+}
+// positions and scales of the block's NT splats -> shared memory (two [NT][3] tiles), then this thread's RawAttr
+template <int NT>
+__device__ __forceinline__ void load_raw_staged(const gab200_forward_args& a, int i, float* smem_xyz, float* smem_scale,
+                                                RawAttr& r) {
+  const int row0 = blockIdx.x * NT, rows = min(NT, a.P - row0);
+  stage_rows_in<NT>(smem_xyz, a.means3D, (size_t)row0, rows, 3, 3);
+  if (a.scales != nullptr) stage_rows_in<NT>(smem_scale, a.scales, (size_t)row0, rows, 3, 3);
+  __syncthreads();
+  if (i < a.P) {
+#pragma unroll
+    for (int k = 0; k < 3; k++) r.x[k] = smem_xyz[3 * threadIdx.x + k];
+    if (a.scales != nullptr) {
+#pragma unroll
+      for (int k = 0; k < 3; k++) r.s[k] = smem_scale[3 * threadIdx.x + k];
+    }
+    if (a.rotations != nullptr) load_quat(a.rotations, (size_t)i, r.q);
+    r.o = a.opacities[i];
+  }
+}
+
+__device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, const RawAttr& raw, Activated& o,
+                                              BindCtx& c) {
+  c.xl = make_float3(raw.x[0], raw.x[1], raw.x[2]);
   // rotation_activation = torch.nn.functional.normalize (eps 1e-12)
-  float qr = a.rotations[4 * (size_t)i], qx = a.rotations[4 * (size_t)i + 1], qy = a.rotations[4 * (size_t)i + 2],
-        qz = a.rotations[4 * (size_t)i + 3];
+  float qr = raw.q[0], qx = raw.q[1], qy = raw.q[2], qz = raw.q[3];
   float n = sqrtf(qr * qr + qx * qx + qy * qy + qz * qz);
   n = fmaxf(n, 1e-12f);
   c.nrm = n;
   c.qn[0] = qr / n; c.qn[1] = qx / n; c.qn[2] = qy / n; c.qn[3] = qz / n;
   quat_to_R(c.qn[0], c.qn[1], c.qn[2], c.qn[3], c.Rl);
-  c.e[0] = expf(a.scales[3 * (size_t)i]);
-  c.e[1] = expf(a.scales[3 * (size_t)i + 1]);
-  c.e[2] = expf(a.scales[3 * (size_t)i + 2]);
-  o.opacity = 1.0f / (1.0f + expf(-a.opacities[i]));
+  c.e[0] = expf(raw.s[0]);
+  c.e[1] = expf(raw.s[1]);
+  c.e[2] = expf(raw.s[2]);
+  o.opacity = 1.0f / (1.0f + expf(-raw.o));
   if (a.binding != nullptr) {
     const int f = a.binding[i];
     c.face = f;
@@ -188,6 +235,11 @@ __device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int 
 #pragma unroll
     for (int k = 0; k < 9; k++) o.R[k] = c.Rl[k];
   }
+}
+__device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, Activated& o, BindCtx& c) {
+  RawAttr raw;
+  load_raw(a, i, raw);
+  bind_activate(a, i, raw, o, c);
 }
 __device__ __forceinline__ void bind_activate(const gab200_forward_args& a, int i, Activated& o) {
   BindCtx c;

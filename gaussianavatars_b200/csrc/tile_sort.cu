@@ -1,5 +1,9 @@
 // tile_sort.cu -- the per-instance half of the tile|depth key sort as a COUNTING sort by tile + a per-tile sort by depth
-// rank, in place of cub::DeviceRadixSort over the instances (which stays available: GAB200_TUNE_TILE_SORT = 1).
+// rank, as an alternative to cub::DeviceRadixSort over the instances (GAB200_TUNE_TILE_SORT = 1 selects it; cub is the
+// default: measured at 100k splats / 1080p the counting form loses -- every instance costs an atomic on its tile's
+// counter in preprocess (RED) and another, with return value, in the emission, and the hot tiles (2000-3000 instances
+// on one address) serialise the L2 atomic unit: preprocess 31 -> 49 us, emission 26 -> 78 us, against a 52 us radix
+// sort.  Kept because it needs no host-side N at all, and as the measured answer to "replace the 5-launch sort").
 //
 // The reference sorts N (tile << 32 | depth) keys with one LSD radix sort.  Stage A
 // (binning.cu / preprocess.cu) already orders the SPLATS by (depth, id); a splat's position in that order -- its depth
@@ -29,7 +33,8 @@ namespace gab {
 // (longest-processing-time-first): the blend kernels walk one tile per CTA / warp pair and a tile's cost is
 // proportional to its list length, so dispatching long lists first removes the tail where a few SMs grind through
 // 2000-deep lists while the rest idle.  Counting sort into 64 length buckets; order_info[0/1] = number of tiles that
-// are "heavy" for the forward / backward blend, order_info[2] = tiles longer than GAB_TILE_SORT_SMEM.
+// are "heavy" for the forward / backward blend, order_info[2] = leading tiles of the order among which the ones longer
+// than GAB_TILE_SORT_SMEM are (0 if there is none).
 __global__ void __launch_bounds__(SCAN_NT) tile_scan_order_kernel(int tiles, const uint32_t* __restrict__ tile_count,
                                                                    uint32_t clamp, uint2* __restrict__ ranges,
                                                                    uint32_t* __restrict__ cursor,
@@ -106,8 +111,10 @@ __global__ void __launch_bounds__(SCAN_NT) tile_scan_order_kernel(int tiles, con
       run += c;
       if (b == (ORDER_NB - 2) - qf) order_info[0] = run;
       if (b == (ORDER_NB - 2) - qb) order_info[1] = run;
+      // bucket 0 holds every list of 1984 entries or more, in no particular order: when any of them is beyond the
+      // shared-memory sort, tile_sort_long_kernel looks at all of bucket 0 (and skips the ones that are not)
+      if (b == 0) order_info[2] = s_long ? c : 0u;
     }
-    order_info[2] = s_long;
   }
   __syncthreads();
   // warp w of round r sees the same tiles as in the counting loop above (same t -> same warp), so its private
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(TSL_NT) tile_sort_long_kernel(const uint2* __r
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t listed = listed_ptr != nullptr ? min(*listed_ptr, (uint32_t)P) : (uint32_t)P;
   const int total_words = (int)((listed + 31u) >> 5);
-  // the long tiles are the first `nlong` of the heaviest-first order
+  // the long tiles are among the first `nlong` of the heaviest-first order
   for (int slot = blockIdx.x; slot < nlong; slot += gridDim.x) {
     const int tile = (int)order[slot];
     const uint2 r = ranges[tile];

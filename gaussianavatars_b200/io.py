@@ -145,3 +145,79 @@ def save_ply(path: str, params: Dict[str, torch.Tensor], binding: Optional[torch
     with open(path, "wb") as f:
         f.write(ply_header(P, names))
         f.write(table.tobytes())
+
+
+# ================================================================================================================
+# flame_param.npz (scene/flame_gaussian_model.py:219-258; layout: SURVEY.md Appendix D)
+# ================================================================================================================
+FLAME_STATIC_KEYS = ("shape", "static_offset")
+FLAME_DYNAMIC_KEYS = ("translation", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "expr", "dynamic_offset")
+
+
+def _npz_members(path: str):
+    """(name, dtype, shape, fortran, data offset) of every member of an UNCOMPRESSED .npz (what np.savez writes):
+    the arrays can then be memory-mapped in place instead of being copied out of the zip."""
+    import struct
+    import zipfile
+
+    from numpy.lib import format as npf
+
+    out = []
+    with zipfile.ZipFile(path) as zf, open(path, "rb") as f:
+        for info in zf.infolist():
+            if info.compress_type != zipfile.ZIP_STORED or not info.filename.endswith(".npy"):
+                return None
+            f.seek(info.header_offset)
+            local = f.read(30)
+            if local[:4] != b"PK\x03\x04":
+                return None
+            n_name, n_extra = struct.unpack("<HH", local[26:30])
+            start = info.header_offset + 30 + n_name + n_extra
+            f.seek(start)
+            major, minor = npf.read_magic(f)
+            shape, fortran, dtype = npf.read_array_header_1_0(f) if (major, minor) == (1, 0) else npf.read_array_header_2_0(f)
+            if dtype.hasobject:
+                return None
+            out.append((info.filename[:-4], dtype, shape, fortran, f.tell()))
+    return out
+
+
+def load_flame_param(path: str, motion_path: Optional[str] = None, device=None, mmap: bool = True) -> Dict[str, torch.Tensor]:
+    """`flame_param.npz` next to a point_cloud.ply -> {shape (300,), expr (T,100), rotation / neck_pose / jaw_pose /
+    translation (T,3), eyes_pose (T,6), static_offset (1,V,3), dynamic_offset (T,V,3)} as tensors
+    (FlameGaussianModel.load_ply, scene/flame_gaussian_model.py:229-236).  With `motion_path`, the static entries
+    (shape, static_offset) are kept and the dynamic ones are replaced by the float32 arrays of that file (:238-256).
+    mmap: the arrays of an uncompressed .npz are mapped in place (the 69 MB demo file opens without being read)."""
+
+    def read(p):
+        members = _npz_members(p) if mmap else None
+        if members is None:
+            z = np.load(p)
+            return {k: z[k] for k in z.files}
+        d = {}
+        for name, dtype, shape, fortran, off in members:
+            n = int(np.prod(shape)) if len(shape) else 1
+            arr = np.memmap(p, dtype=dtype, mode="r", offset=off, shape=(n,)) if n else np.zeros((0,), dtype)
+            d[name] = arr.reshape(shape, order="F" if fortran else "C")
+        return d
+
+    def to_t(a):
+        t = torch.from_numpy(np.array(a, copy=True) if device is None else np.asarray(a))
+        return t if device is None else t.to(device)
+
+    fp = {k: to_t(v) for k, v in read(path).items()}
+    if motion_path is not None:
+        mo = {k: to_t(v) for k, v in read(motion_path).items() if v.dtype == np.float32}
+        fp = {**{k: fp[k] for k in FLAME_STATIC_KEYS}, **{k: mo[k] for k in FLAME_DYNAMIC_KEYS}}
+    return fp
+
+
+def save_flame_param(path: str, flame_param: Dict[str, torch.Tensor]) -> str:
+    """FlameGaussianModel.save_ply's second half (scene/flame_gaussian_model.py:219-224): np.savez of the tensors
+    (moved to the CPU), key order preserved.  `path` is either the .npz itself or the point_cloud.ply it sits beside."""
+    if path.endswith(".ply"):
+        path = os.path.join(os.path.dirname(path), "flame_param.npz")
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    arrays = {k: (v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)) for k, v in flame_param.items()}
+    np.savez(path, **arrays)
+    return path

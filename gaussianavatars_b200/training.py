@@ -126,3 +126,78 @@ class Adam(torch.optim.Optimizer):
                 N.check(N.lib().gab200_adam_step(len(segs), arr, step, beta1, beta2, eps, C.c_void_p(stream)),
                         "gab200_adam_step")
         return loss
+
+
+# ================================================================================================================
+# position / scale regularisers of the mesh-bound training step (train.py:134-146), loss + gradient in one launch each
+# ================================================================================================================
+class _BindingRegularizers(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, _xyz, _scaling, face_scaling, radii, binding, thr_xyz, thr_scale, lam_xyz, lam_scale, metric_xyz,
+                metric_scale):
+        device = _xyz.device
+        if device.type != "cuda":
+            raise RuntimeError("gaussianavatars_b200 has no CPU path: tensors must be CUDA tensors")
+        for t, n in ((_xyz, "_xyz"), (_scaling, "_scaling")):
+            if t.dtype != torch.float32 or t.shape != (_xyz.shape[0], 3):
+                raise TypeError(f"{n} must be a float32 (P, 3) tensor")
+        P = _xyz.shape[0]
+        x = _xyz if _xyz.is_contiguous() else _xyz.contiguous()
+        s = _scaling if _scaling.is_contiguous() else _scaling.contiguous()
+        r = radii if radii.dtype == torch.int32 else radii.to(torch.int32)   # a bool visibility_filter works as well
+        r = r if r.is_contiguous() else r.contiguous()
+        if r.numel() != P:
+            raise ValueError("radii / visibility_filter must have one entry per splat")
+        a = N.RegularizeArgs()
+        a.abi_version, a.P = N.ABI_VERSION, P
+        a.metric_xyz, a.metric_scale = int(bool(metric_xyz)), int(bool(metric_scale))
+        a.threshold_xyz, a.threshold_scale = float(thr_xyz), float(thr_scale)
+        a.lambda_xyz, a.lambda_scale = float(lam_xyz), float(lam_scale)
+        a.xyz, a.scaling, a.radii = x.data_ptr(), s.data_ptr(), r.data_ptr()
+        keep = [x, s, r]
+        if binding is not None:
+            b = binding if binding.dtype == torch.int32 else binding.to(torch.int32)
+            fs = face_scaling.reshape(-1)
+            fs = fs if fs.is_contiguous() else fs.contiguous()
+            a.binding, a.face_scaling = b.data_ptr(), fs.data_ptr()
+            keep += [b, fs]
+        loss = torch.empty(3, dtype=torch.float32, device=device)
+        sums = torch.empty(3, dtype=torch.float64, device=device)
+        a.loss, a.sums = loss.data_ptr(), sums.data_ptr()
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_regularize_forward(C.byref(a), C.c_void_p(stream)), "gab200_regularize_forward")
+        ctx.args, ctx.keep, ctx.sums = a, keep, sums
+        ctx.face_shape = None if face_scaling is None else face_scaling.shape
+        ctx.want_face = binding is not None and face_scaling is not None and ctx.needs_input_grad[2] and \
+            (metric_xyz or metric_scale)
+        ctx.mark_non_differentiable(loss)
+        return loss[0], loss[1], loss
+
+    @staticmethod
+    def backward(ctx, g_xyz, g_scale, _g_all):
+        a = ctx.args
+        device = ctx.keep[0].device
+        P = a.P
+        gx = torch.empty((P, 3), dtype=torch.float32, device=device)
+        gs = torch.empty((P, 3), dtype=torch.float32, device=device)
+        gf = torch.zeros(ctx.face_shape, dtype=torch.float32, device=device) if ctx.want_face else None
+        z = torch.zeros((), dtype=torch.float32, device=device)
+        g = torch.stack((g_xyz if g_xyz is not None else z, g_scale if g_scale is not None else z)).float().contiguous()
+        a.grad_xyz, a.grad_scaling, a.grad_face_scaling = gx.data_ptr(), gs.data_ptr(), N.ptr(gf)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_regularize_backward(C.byref(a), g.data_ptr(), C.c_void_p(stream)),
+                    "gab200_regularize_backward")
+        return gx, gs, gf, None, None, None, None, None, None, None, None
+
+
+def binding_regularizers(_xyz, _scaling, radii, binding=None, face_scaling=None, threshold_xyz=1.0, threshold_scale=0.6,
+                         lambda_xyz=1e-2, lambda_scale=1.0, metric_xyz=False, metric_scale=False, return_count=False):
+    """`losses['xyz']`, `losses['scale']` of the reference training step (train.py:134-146; defaults
+    arguments/__init__.py:100-105), differentiable w.r.t. `_xyz`, `_scaling` (and `face_scaling` in the metric
+    variants).  `radii` is the rendered frame's radii (or its `visibility_filter`).  A training step that adds these
+    two to the photometric loss never calls `get_scaling` / boolean-mask indexing."""
+    lx, ls, all_ = _BindingRegularizers.apply(_xyz, _scaling, face_scaling, radii, binding, threshold_xyz, threshold_scale,
+                                              lambda_xyz, lambda_scale, metric_xyz, metric_scale)
+    return (lx, ls, all_[2]) if return_count else (lx, ls)

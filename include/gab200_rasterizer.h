@@ -177,7 +177,7 @@ typedef struct gab200_frame_state {
   uint32_t depth_key_max;
   int32_t depth_sort_path;    /* 0: radix sort (no hint); 1: bucket sort; 2: bucket sort overflowed, radix sort redone */
   int32_t attempts;           /* 1 + number of times stages were re-enqueued (GAB200_SYNC_LATE only; else 1) */
-  int32_t tile_sort_path;     /* 0: counting sort by tile + per-tile rank sort; 1: cub::DeviceRadixSort over the instances */
+  int32_t tile_sort_path;     /* 0: cub::DeviceRadixSort over the instances; 1: counting sort by tile + per-tile rank sort */
   int32_t reserved0;
   const uint32_t* device_counters; /* GAB200_NUM_COUNTERS words inside the geometry buffer (valid as long as it is) */
 } gab200_frame_state;
@@ -306,6 +306,74 @@ typedef struct gab200_adam_segment {
 int32_t gab200_adam_step(int32_t num_segments, const gab200_adam_segment* segments, int64_t step, double beta1,
                          double beta2, double eps, void* stream);
 
+/* The position / scale regularisers of the mesh-bound training step (train.py:134-146), loss and gradient in one
+ * launch each.  vis = radii > 0 of the frame just rendered.  loss[3] receives {xyz term, scale term, visible count};
+ * sums: 3 doubles of device scratch shared by the forward and its backward.  The backward writes grad_xyz /
+ * grad_scaling [P,3] in full (zeros for invisible splats) and ADDS into grad_face_scaling [F] (metric_* only; the
+ * caller zero-fills it); g_out[2] = upstream gradients of the two terms (device). */
+typedef struct gab200_regularize_args {
+  uint32_t abi_version;
+  int32_t P;
+  int32_t metric_xyz, metric_scale;
+  float threshold_xyz, threshold_scale, lambda_xyz, lambda_scale;
+  const float *xyz, *scaling;          /* raw _xyz, _scaling [P,3] */
+  const int32_t* radii;                /* [P] */
+  const int32_t* binding;              /* [P] or NULL */
+  const float* face_scaling;           /* [F] */
+  float* loss;                         /* [3] */
+  double* sums;                        /* [3] */
+  float *grad_xyz, *grad_scaling, *grad_face_scaling;   /* backward only */
+} gab200_regularize_args;
+int32_t gab200_regularize_forward(const gab200_regularize_args* args, void* stream);
+int32_t gab200_regularize_backward(const gab200_regularize_args* args, const float* g_out, void* stream);
+
+/* densify_and_prune of the splat arrays with the Adam-state surgery fused.  Replaces
+ * GaussianModel.densify_and_prune (scene/gaussian_model.py:503-519 -> densify_and_clone :481-501, densify_and_split
+ * :451-479, prune_points :371-397) together with the optimizer surgery it drives (:334-369, :399-424) and the
+ * binding / binding_counter bookkeeping (:375-380, :395-397, :472-474, :495-497).  Two calls, because the caller has to
+ * size the outputs:
+ *   gab200_densify_plan   classifies every splat and scans the result; performs ONE stream synchronisation and leaves
+ *                         totals_host = {kept originals, kept clones, kept child pairs, split parents}.
+ *                         Output rows: P' = totals[0] + totals[1] + 2 * totals[2], in the reference's order
+ *                         (originals, clones, first children, second children).
+ *   gab200_densify_apply  gathers the six parameter arrays and their exp_avg / exp_avg_sq into the outputs (new rows get
+ *                         zero moments), samples the children (noise: [2 * totals[3], 3] STANDARD normal values, rows
+ *                         [0, S) for the first child of the S split parents in index order, [S, 2S) for the second --
+ *                         exactly what torch.normal(mean=0, std=...) draws), and rebuilds binding / binding_counter.
+ * The densification statistics (xyz_gradient_accum, denom, max_radii2D) of the result are all zero in the reference
+ * (densification_postfix :447-449): the caller allocates zeros of length P'. */
+typedef struct gab200_densify_args {
+  uint32_t abi_version;
+  int32_t P, num_faces;
+  int32_t sh_rest_width;   /* floats per splat of _features_rest: 3 * (M - 1) */
+  float grad_threshold, min_opacity, extent, percent_dense;
+  float max_screen_size;   /* <= 0: None */
+  const float *xyz, *rotation, *scaling, *opacity, *f_dc, *f_rest;   /* raw parameters [P, 3|4|3|1|3|sh_rest_width] */
+  const float* exp_avg[6];     /* Adam moments in the order xyz, rotation, scaling, opacity, f_dc, f_rest; NULL = none */
+  const float* exp_avg_sq[6];
+  const float *xyz_gradient_accum, *denom;   /* [P] */
+  const int32_t* binding;          /* [P] or NULL (plain GaussianModel) */
+  const int32_t* binding_counter;  /* [F] */
+  const float* face_scaling;       /* [F] */
+  void* scratch;                   /* device, gab200_densify_scratch_bytes(P, F) bytes, 256-byte aligned; shared by both calls */
+  uint32_t* totals_host;           /* HOST (pinned), 4 words */
+} gab200_densify_args;
+typedef struct gab200_densify_out {
+  int32_t P_out, n_child_rows;     /* totals[0] + totals[1] + 2 totals[2];  2 totals[2] */
+  float *xyz, *rotation, *scaling, *opacity, *f_dc, *f_rest;
+  float* exp_avg[6];
+  float* exp_avg_sq[6];
+  int32_t* binding;                /* [P_out] or NULL */
+  int32_t* binding_counter;        /* [F] or NULL */
+  const float* noise;              /* [2 * totals[3], 3] */
+  int32_t* src_scratch;            /* [P_out] device scratch */
+  uint8_t* kind_scratch;           /* [P_out] */
+  int32_t* noise_row_scratch;      /* [totals[2]] */
+} gab200_densify_out;
+size_t gab200_densify_scratch_bytes(int32_t P, int32_t num_faces);
+int32_t gab200_densify_plan(const gab200_densify_args* args, void* stream);
+int32_t gab200_densify_apply(const gab200_densify_args* args, const gab200_densify_out* out, void* stream);
+
 /* Debug/parity access to a finished forward: copies the sorted (key,value) stream and tile ranges to caller
  * DEVICE buffers: keys [N] u64, values [N] u32, ranges [tiles,2] u32. Any may be NULL. */
 int32_t gab200_export_binning(const gab200_forward_args* args, const gab200_frame_state* state, uint64_t* keys,
@@ -345,9 +413,11 @@ enum {
                                   for 5 CTAs per SM; 6 = 1 with specialised bodies; 7 = 2 for 6 CTAs per SM.
                                   Measured at the headline size (profiles/r02/bwd_variants.jsonl): 211 / 198 / 179 /
                                   175 / 182 / 185 / 186 / 211 us */
-  GAB200_TUNE_TILE_SORT = 4,   /* per-instance sort by tile: 0 (default) counting sort + per-tile rank sort (2-3 launches,
-                                  csrc/tile_sort.cu); 1 cub::DeviceRadixSort::SortPairs over the instances (5 launches +
-                                  tile-range detection).  Identical sorted streams. */
+  GAB200_TUNE_TILE_SORT = 4,   /* per-instance sort by tile: 0 (default) cub::DeviceRadixSort::SortPairs over the instances
+                                  (5 launches + tile-range detection); 1 counting sort by tile + per-tile rank sort
+                                  (csrc/tile_sort.cu: 3 launches, no memsets).  Identical sorted streams; at the headline
+                                  size the counting form is SLOWER (same-address atomics on the hot tiles' counters:
+                                  preprocess +18 us, emission 26 -> 78 us; profiles/r02/tile_sort_counting_vs_cub.json) */
   GAB200_NUM_TUNABLES = 8
 };
 int32_t gab200_tune(int32_t knob, int32_t value);

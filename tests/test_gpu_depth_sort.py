@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 def tile_sort_implementation(request):
     from gaussianavatars_b200 import _native as N
 
-    N.tune(N.TUNE_TILE_SORT, 0 if request.param.startswith("counting") else 1)
+    N.tune(N.TUNE_TILE_SORT, 1 if request.param.startswith("counting") else 0)
     yield
     N.tune(N.TUNE_TILE_SORT, 0)
 

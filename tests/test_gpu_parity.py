@@ -14,7 +14,7 @@ def tile_sort_implementation(request):
     (include/gab200_rasterizer.h GAB200_TUNE_TILE_SORT): the sorted stream, image and gradients must not depend on it."""
     from gaussianavatars_b200 import _native as N
 
-    N.tune(N.TUNE_TILE_SORT, 0 if request.param.startswith("counting") else 1)
+    N.tune(N.TUNE_TILE_SORT, 1 if request.param.startswith("counting") else 0)
     yield
     N.tune(N.TUNE_TILE_SORT, 0)
 

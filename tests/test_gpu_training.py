@@ -209,3 +209,68 @@ def test_photometric_loss_accepts_a_batch_like_the_reference_ssim():
     assert abs(float(total.detach()) - 0.5 * (singles[0] + singles[1])) < 1e-6
     assert x.grad.shape == imgs.shape
     assert torch.allclose(x.grad, 0.5 * torch.stack(grads), rtol=1e-5, atol=1e-12)
+
+
+@pytest.mark.parametrize("metric_xyz,metric_scale,lam_scale", [(False, False, 1.0), (True, True, 1.0), (False, True, 0.5),
+                                                              (True, False, 0.0)])
+def test_binding_regularizers_match_the_training_step_lines(metric_xyz, metric_scale, lam_scale):
+    """train.py:134-146 restated in eager float64 torch (the reference evaluates these lines inline in its loop)."""
+    import gaussianavatars_b200 as g
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(0)
+    P, F = 50_000, 977
+    xyz = (torch.randn(P, 3, generator=gen) * 0.9).to(dev).requires_grad_(True)
+    sc = (torch.randn(P, 3, generator=gen) * 0.8 - 0.6).to(dev).requires_grad_(True)
+    fs = (torch.rand(F, 1, generator=gen) * 2.0 + 0.2).to(dev).requires_grad_(True)
+    binding = torch.randint(0, F, (P,), generator=gen).to(dev)
+    radii = torch.randint(0, 3, (P,), generator=gen, dtype=torch.int32).to(dev)
+    thr_x, thr_s, lam_x = 1.0, 0.6, 1e-2
+    lx, ls, cnt = g.binding_regularizers(xyz, sc, radii, binding, fs, thr_x, thr_s, lam_x, lam_scale, metric_xyz, metric_scale,
+                                         return_count=True)
+    (3.0 * lx + 0.5 * ls).backward()
+    # reference formulas
+    X, S, FS = (t.detach().double().requires_grad_(True) for t in (xyz, sc, fs))
+    vis = radii > 0
+    relu = torch.nn.functional.relu
+    if metric_xyz:
+        rx = relu((X * FS[binding])[vis] - thr_x).norm(dim=1).mean() * lam_x
+    else:
+        rx = relu(X[vis].norm(dim=1) - thr_x).mean() * lam_x
+    if lam_scale != 0:
+        if metric_scale:
+            rs = relu((torch.exp(S) * FS[binding])[vis] - thr_s).norm(dim=1).mean() * lam_scale
+        else:
+            rs = relu(torch.exp(S[vis]) - thr_s).norm(dim=1).mean() * lam_scale
+    else:
+        rs = torch.zeros((), dtype=torch.float64, device=dev)
+    (3.0 * rx + 0.5 * rs).backward()
+    assert int(cnt) == int(vis.sum())
+    assert abs(float(lx) - float(rx)) <= 2e-6 * abs(float(rx)) + 1e-12
+    assert abs(float(ls) - float(rs)) <= 2e-6 * abs(float(rs)) + 1e-12
+    for got, ref, name in ((xyz.grad, X.grad, "xyz"), (sc.grad, S.grad, "scaling")):
+        ref = torch.zeros_like(got, dtype=torch.float64) if ref is None else ref
+        assert torch.allclose(got.double(), ref, rtol=1e-5, atol=1e-12), name
+        assert float(got[~vis].abs().sum()) == 0.0
+    if metric_xyz or (metric_scale and lam_scale != 0):
+        assert torch.allclose(fs.grad.double(), FS.grad, rtol=2e-4, atol=1e-10), "face_scaling"
+    else:
+        assert fs.grad is None
+
+
+def test_binding_regularizers_on_a_rendered_frame_and_unbound():
+    """With the radii of a real frame, and the plain-model form (no binding: non-metric terms only)."""
+    import gaussianavatars_b200 as g
+
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    xyz = torch.randn(1000, 3, generator=gen).to(dev).requires_grad_(True)
+    sc = torch.randn(1000, 3, generator=gen).to(dev).requires_grad_(True)
+    vis = (torch.rand(1000, generator=gen) > 0.3).to(dev)
+    lx, ls = g.binding_regularizers(xyz, sc, vis)
+    (lx + ls).backward()
+    rx = torch.nn.functional.relu(xyz.detach()[vis].norm(dim=1) - 1.0).mean() * 1e-2
+    assert abs(float(lx) - float(rx)) < 1e-7 and xyz.grad.shape == (1000, 3)
+    # nothing visible: mean over an empty set is nan in the reference, and here
+    lx0, _ = g.binding_regularizers(xyz.detach(), sc.detach(), torch.zeros(1000, dtype=torch.bool, device=dev))
+    assert torch.isnan(lx0)

@@ -39,7 +39,9 @@ def test_ctypes_structs_match_the_c_layout(tmp_path):
     from gaussianavatars_b200 import _native as N
 
     fields = {"gab200_forward_args": N.ForwardArgs, "gab200_frame_state": N.FrameState, "gab200_backward_args": N.BackwardArgs,
-              "gab200_photometric_args": N.PhotometricArgs, "gab200_adam_segment": N.AdamSegment}
+              "gab200_photometric_args": N.PhotometricArgs, "gab200_adam_segment": N.AdamSegment,
+              "gab200_densify_args": N.DensifyArgs, "gab200_densify_out": N.DensifyOut,
+              "gab200_regularize_args": N.RegularizeArgs}
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{HEADER}"', "int main(){"]
     for cname, ct in fields.items():
         lines.append(f'printf("{cname} %zu\\n", sizeof({cname}));')

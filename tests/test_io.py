@@ -135,3 +135,60 @@ def test_demo_avatar_of_the_reference_round_trips_byte_for_byte(tmp_path):
     h1.update(open(DEMO, "rb").read())
     h2.update(out.read_bytes())
     assert h1.hexdigest() == h2.hexdigest()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# flame_param.npz
+# ------------------------------------------------------------------------------------------------------------
+DEMO_NPZ = "/root/reference/media/306/flame_param.npz"
+
+
+def _fake_flame(T, V=37, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=g)  # noqa: E731
+    return {"shape": r(300), "expr": r(T, 100), "rotation": r(T, 3), "neck_pose": r(T, 3), "jaw_pose": r(T, 3),
+            "eyes_pose": r(T, 6), "translation": r(T, 3), "static_offset": r(1, V, 3), "dynamic_offset": r(T, V, 3)}
+
+
+@pytest.mark.parametrize("mmap", [True, False])
+def test_flame_param_round_trip_and_motion_override(tmp_path, mmap):
+    fp = _fake_flame(5)
+    p = gio.save_flame_param(str(tmp_path / "a" / "point_cloud.ply"), fp)
+    assert p.endswith("flame_param.npz") and os.path.exists(p)
+    back = gio.load_flame_param(p, mmap=mmap)
+    assert list(back) == list(fp)
+    for k in fp:
+        assert back[k].dtype == torch.float32 and torch.equal(back[k], fp[k]), k
+    # np.load agrees (the writer is np.savez, the reference's)
+    z = np.load(p)
+    assert z.files == list(fp) and all(np.array_equal(z[k], fp[k].numpy()) for k in fp)
+    # motion sequence: static entries kept, dynamic ones replaced, non-float32 entries of the motion file ignored
+    mo = _fake_flame(9, seed=1)
+    mp = str(tmp_path / "motion.npz")
+    np.savez(mp, **{k: v.numpy() for k, v in mo.items()}, frame_id=np.arange(9))
+    mixed = gio.load_flame_param(p, motion_path=mp, mmap=mmap)
+    assert set(mixed) == set(fp)
+    for k in gio.FLAME_STATIC_KEYS:
+        assert torch.equal(mixed[k], fp[k])
+    for k in gio.FLAME_DYNAMIC_KEYS:
+        assert torch.equal(mixed[k], mo[k]) and mixed[k].shape[0] == 9
+
+
+@pytest.mark.skipif(not os.path.exists(DEMO_NPZ), reason="/root/reference is not mounted here")
+def test_flame_param_of_the_demo_avatar(tmp_path):
+    """media/306/flame_param.npz: mapped in place == np.load, and re-saved member by member byte-identical (the .npy
+    payloads; zip timestamps differ between any two np.savez calls)."""
+    import zipfile
+
+    fp = gio.load_flame_param(DEMO_NPZ)
+    assert fp["expr"].shape == (1119, 100) and fp["static_offset"].shape == (1, 5143, 3) and fp["shape"].shape == (300,)
+    assert fp["dynamic_offset"].shape == (1119, 5143, 3) and fp["eyes_pose"].shape == (1119, 6)
+    z = np.load(DEMO_NPZ)
+    small = [k for k in z.files if k != "dynamic_offset"]
+    for k in small:
+        assert np.array_equal(fp[k].numpy(), z[k]), k
+    out = gio.save_flame_param(str(tmp_path / "flame_param.npz"), {k: fp[k] for k in small})
+    with zipfile.ZipFile(DEMO_NPZ) as a, zipfile.ZipFile(out) as b:
+        assert [i.filename for i in b.infolist()] == [k + ".npy" for k in small]
+        for k in small:
+            assert a.read(k + ".npy") == b.read(k + ".npy"), k
