@@ -1,4 +1,6 @@
-// A non-Python caller of the C ABI (include/gab200_rasterizer.h): renders P random splats once and runs the backward.
+// A non-Python caller of the C ABI (include/gab200_rasterizer.h): renders P random splats (a first frame with the
+// mid-frame sync, a second one sync-free on the hints the first left behind -- identical image), runs the backward,
+// and with a path argument dumps inputs and results for tests/test_gpu_dropin.py to compare with the Python surface.
 // No torch: device memory comes from cudaMalloc, the three scratch buffers from the allocation callbacks -- what
 // INTEGRATION.md section 3 describes.  Build (from the repo root, after `python -m gaussianavatars_b200.build`):
 //   nvcc -gencode arch=compute_100a,code=sm_100a -std=c++17 -Iinclude examples/abi_forward_backward.cu \
@@ -39,7 +41,14 @@ static T* upload(const std::vector<T>& h) {
   return d;
 }
 
-int main() {
+template <typename T>
+static bool dump(std::FILE* f, const T* dev, size_t n) {
+  std::vector<T> h(n);
+  if (cudaMemcpy(h.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+  return std::fwrite(h.data(), sizeof(T), n, f) == n;
+}
+
+int main(int argc, char** argv) {
   const int P = 20000, W = 640, H = 360;
   std::srand(1);
   auto rnd = [] { return (float)std::rand() / (float)RAND_MAX; };
@@ -83,6 +92,26 @@ int main() {
   std::printf("forward: %lld (splat, tile) instances, depth-sort path %d, key range [%08x, %08x]\n", (long long)n,
               st.depth_sort_path, st.depth_key_min, st.depth_key_max);
 
+  // second frame: the first one's instance count and depth-key range are the hints; nothing waits for the GPU until
+  // the call's final check (GAB200_SYNC_LATE).  Same inputs -> the image must be bit-identical.
+  std::vector<float> img1((size_t)3 * W * H), img2((size_t)3 * W * H);
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaMemcpy(img1.data(), out, img1.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  a.sync_mode = GAB200_SYNC_LATE;
+  a.binning_hint = (int32_t)(n + n / 4 + 4096);
+  a.depth_hint_lo = st.depth_key_min;
+  a.depth_hint_hi = st.depth_key_max;
+  a.frame_seq = 2;
+  const int64_t n2 = gab200_forward(&a, &st, stream);
+  if (n2 < 0) { std::fprintf(stderr, "gab200_forward (2): %s\n", gab200_status_string((int32_t)n2)); return 1; }
+  CK(cudaStreamSynchronize(stream));
+  CK(cudaMemcpy(img2.data(), out, img2.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  size_t differing = 0;
+  for (size_t i = 0; i < img1.size(); i++) differing += img1[i] != img2[i] ? 1 : 0;
+  std::printf("second frame: %lld instances, depth-sort path %d, attempts %d, capacity %lld, pixels differing from frame 1: %zu\n",
+              (long long)n2, st.depth_sort_path, st.attempts, (long long)st.binning_capacity, differing);
+  if (n2 != n || differing != 0) { std::fprintf(stderr, "sync-free frame differs from the first\n"); return 1; }
+
   // backward of sum(image): dL/dimage = 1
   std::vector<float> ones((size_t)3 * W * H, 1.f);
   gab200_backward_args b{};
@@ -103,6 +132,20 @@ int main() {
   double s = 0;
   for (float v : h_op) s += v;
   std::printf("backward: sum dL/dopacity = %.6f; %lld library launches so far\n", s, (long long)gab200_launch_count());
-  // the next frame would pass  a.binning_hint = 1.25 n  and  a.depth_hint_lo/hi = st.depth_key_min/max (widened)
+  if (argc > 1) {  // inputs + results, raw little-endian: the Python surface must reproduce them
+    std::FILE* f = std::fopen(argv[1], "wb");
+    if (!f) { std::perror(argv[1]); return 1; }
+    const int32_t head[4] = {P, W, H, (int32_t)n2};
+    const float cam[2] = {tanx, tany};
+    bool ok = std::fwrite(head, sizeof(head), 1, f) == 1 && std::fwrite(cam, sizeof(cam), 1, f) == 1;
+    ok = ok && std::fwrite(means.data(), 4, means.size(), f) == means.size() &&
+         std::fwrite(scales.data(), 4, scales.size(), f) == scales.size() && std::fwrite(rots.data(), 4, rots.size(), f) == rots.size() &&
+         std::fwrite(opac.data(), 4, opac.size(), f) == opac.size() && std::fwrite(rgb.data(), 4, rgb.size(), f) == rgb.size() &&
+         std::fwrite(view.data(), 4, 16, f) == 16 && std::fwrite(proj.data(), 4, 16, f) == 16;
+    ok = ok && dump(f, out, (size_t)3 * W * H) && dump(f, radii, (size_t)P) && dump(f, g_means, (size_t)3 * P) &&
+         dump(f, g_op, (size_t)P) && dump(f, g_col, (size_t)3 * P) && dump(f, g_sc, (size_t)3 * P);
+    std::fclose(f);
+    if (!ok) { std::fprintf(stderr, "dump failed\n"); return 1; }
+  }
   return 0;
 }
