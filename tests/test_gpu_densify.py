@@ -71,7 +71,7 @@ def test_150k_splats_against_the_gather_plan_oracle():
                  torch.rand(params[n].shape, generator=gen).numpy() * 1e-4) for n in od.NAMES}
     stats = {"xyz_gradient_accum": (torch.rand(P, 1, generator=gen) * 6e-4).numpy(),
              "denom": torch.randint(0, 3, (P, 1), generator=gen).float().numpy(), "max_radii2D": np.zeros(P, np.float32)}
-    hyper = np.array([0.0002, 0.005, 0.6, 20.0, 0.01])
+    hyper = np.array([0.0002, 0.005, 0.1, 20.0, 0.01])
     pl = od.plan(params, stats, hyper, binding, counter, fs)
     S = int(pl["split"].sum())
     assert S > 1000 and pl["clone"].sum() > 1000
