@@ -171,12 +171,29 @@ class ClockSampler:
 # CPU arm: the oracle port on the host cores (bench.py's cpu_baseline and --impl reference)
 # ---------------------------------------------------------------------------------------------------------------
 def host_cpus():
-    """CPUs this process may run on (the affinity mask of the container, not the machine's os.cpu_count(): forcing 128
-    OpenMP threads onto a smaller mask made the CPU arm 10x slower)."""
+    """CPUs this process can actually use: the smaller of the affinity mask and the cgroup CPU quota.  The GPU boxes
+    show 128 logical CPUs under a quota of 16 (cpu.max = 1600000 100000); 128 OpenMP threads throttled onto 16 CPUs'
+    worth of time made the eager binding getters 700x slower (3.5 s instead of 5 ms per frame, profiles/r02/
+    cpu_threads_probe.jsonl), and the C oracle shares torch's OpenMP runtime, so one number serves both."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
+        n = len(os.sched_getaffinity(0))
     except Exception:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    for path in ("/sys/fs/cgroup/cpu.max", "/sys/fs/cgroup/cpu/cpu.cfs_quota_us"):
+        try:
+            txt = open(path).read().split()
+            if path.endswith("cpu.max"):
+                if txt[0] != "max":
+                    n = min(n, max(1, -(-int(txt[0]) // int(txt[1]))))
+            else:
+                quota = int(txt[0])
+                period = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+                if quota > 0:
+                    n = min(n, max(1, -(-quota // period)))
+            break
+        except Exception:
+            continue
+    return max(1, n)
 
 
 def cpu_frames(params, verts, faces, cams, frames, threads=None):
@@ -187,16 +204,11 @@ def cpu_frames(params, verts, faces, cams, frames, threads=None):
     from oracle import binding as ob
     from oracle import rasterizer as orc
 
-    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: say explicitly how many threads this arm gets.
-    # The C oracle (its own libgomp) gets every logical CPU; torch's intra-op pool keeps its default (one thread per
-    # physical core) unless the launcher forced it to 1 -- two pools of spinning threads on every logical CPU
-    # oversubscribe the box (measured: the eager binding getters went from 19 ms to 3.5 s per frame).
-    cpus = host_cpus()
-    orc.set_threads(threads or cpus)
-    if threads:
-        torch.set_num_threads(threads)
-    elif torch.get_num_threads() == 1 and cpus > 1:
-        torch.set_num_threads(max(1, cpus // 2))
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers: say explicitly how many threads this arm gets
+    # (host_cpus(): what the container may really use).
+    cpus = threads or host_cpus()
+    torch.set_num_threads(cpus)
+    orc.set_threads(cpus)
     bg = np.ones(3, np.float32)
     gout = torch.randn(3, HEIGHT, WIDTH, generator=torch.Generator().manual_seed(1)).numpy()
     from gaussianavatars_b200 import synthetic as syn
@@ -646,7 +658,7 @@ def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gou
         ob.get_opacity(params["_opacity"])
         ob.get_features(params["_features_dc"], params["_features_rest"])
         tb1.append(time.perf_counter() - t0)
-    torch.set_num_threads(default_threads)
+    torch.set_num_threads(cores)
     out["cpu_baseline"] = {"value": 1.0 / sec, "unit": "frames/s", "cores": cores, "kind": "port",
                            "sample": f"{frames} full frames of the same workload (eager torch binding getters + "
                                      f"C oracle rasterizer fwd+bwd, OpenMP x{cores}); the port is the parity CHECKER "
