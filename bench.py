@@ -356,29 +356,6 @@ def main():
     _, _, _, n_inst = R.export_last_binning()
     R.keep_last_state(False)
 
-    # ---- the step as ONE CUDA graph --------------------------------------------------------------------------------
-    from gaussianavatars_b200.graph import GraphedFrame, camera_block
-
-    cam_blocks_dev = [camera_block(c) for c in cams_dev]
-    c0 = my_cams[0]
-    use_graph = not args.no_graph and symm is None
-    frame = None
-    if use_graph:
-        frame = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev,
-                             after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
-        frame.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
-        frame.capture()
-
-    def step_resident(i):
-        if frame is None:
-            return step_eager(i)
-        frame.set_inputs(camera=cam_blocks_dev[i % len(cam_blocks_dev)], verts=posed[i % len(posed)].detach())
-        frame.run()
-
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-    barrier()
-
     # ---- timed region: HBM-resident, L2 flushed between steps, per-step CUDA events -------------------------
     K = args.steps
 
@@ -404,15 +381,50 @@ def main():
         N.stage_timing(False)
         return sum(s.elapsed_time(e) for s, e in zip(starts, ends)), N.launch_count() - l0, clk_, w1 - w0, st_, hu_
 
-    # pass 1 -- the headline number: nothing but the K steps inside the event pairs
-    ms_total, _, clk, wall_timed, _, _ = timed_pass(step_resident, False)
-    overflow_steps = bool(frame is not None and frame.overflowed(wait=True))
-    # pass 2 -- the eager drop-in surface, same K flushed steps (launch count of one eager step = kernels per frame)
+    # eager passes FIRST (before any NCCL kernel is captured into a graph: afterwards the eager all-reduce of a fresh
+    # buffer per step took 9.8 ms at N = 2, profiles/r02/bench_n2_first.json -- buffer registration churn)
+    # pass A -- the eager drop-in surface, K flushed steps (launch count of one eager step = kernels per frame)
     ms_eager, launches_eager, _, _, _, host_us = timed_pass(step_eager, False)
-    # pass 3 -- eager again with the library's per-stage CUDA events switched on (two event records per stage per step
-    # perturb the pipeline, so they stay out of passes 1-2): per-kernel durations for the roofline line and stage_ms
+    # pass B -- eager again with the library's per-stage CUDA events switched on (two event records per stage per step
+    # perturb the pipeline, so they stay out of the other passes): per-kernel durations for the roofline line and stage_ms
     ms_instrumented, _, _, _, stage, _ = timed_pass(step_eager, True)
     launches = launches_eager  # a graph replay launches the same kernels (they were captured from this very step)
+
+    # ---- the step as ONE CUDA graph --------------------------------------------------------------------------------
+    from gaussianavatars_b200.graph import GraphedFrame, camera_block
+
+    cam_blocks_dev = [camera_block(c) for c in cams_dev]
+    c0 = my_cams[0]
+    use_graph = not args.no_graph and symm is None
+    frame = None
+    graph_note = None
+    if use_graph:
+        try:
+            frame = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev,
+                                 after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
+            frame.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
+            frame.capture()
+        except Exception as e:  # e.g. a fabric on which NCCL cannot be captured: measure the eager step instead, and say so
+            frame, use_graph, graph_note = None, False, f"graph capture failed ({type(e).__name__}: {e}); eager step timed"
+        if world > 1:  # every rank must take the same path (a captured all-reduce cannot meet an eager one)
+            flag = torch.tensor([1.0 if use_graph else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if float(flag) == 0.0 and use_graph:
+                frame, use_graph, graph_note = None, False, "another rank could not capture the step; eager step timed"
+
+    def step_resident(i):
+        if frame is None:
+            return step_eager(i)
+        frame.set_inputs(camera=cam_blocks_dev[i % len(cam_blocks_dev)], verts=posed[i % len(posed)].detach())
+        frame.run()
+
+    for i in range(max(args.warmup, 3)):
+        step_resident(i)
+    barrier()
+
+    # the headline number: nothing but the K steps inside the event pairs
+    ms_total, _, clk, wall_timed, _, _ = timed_pass(step_resident, False)
+    overflow_steps = bool(frame is not None and frame.overflowed(wait=True))
 
     # ---- warm-L2 variant (no flush), whole-loop events: what a training loop actually sees -------------------
     barrier()
@@ -554,8 +566,7 @@ def main():
     ms_total, ms_warm, ms_e2e = max_over_ranks(ms_total), max_over_ranks(ms_warm), max_over_ranks(ms_e2e)
     ms_eager, ms_instrumented = max_over_ranks(ms_eager), max_over_ranks(ms_instrumented)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish(world, dev)
         return
 
     fps = world * K / (ms_total / 1e3)
@@ -593,7 +604,7 @@ def main():
                    "faces": F, "instances_per_frame": int(n_inst), "binning": "exact" if args.exact_binning else "culled",
                    "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded dp{world}",
                    "step": ("one CUDA-graph replay (face frame + fused fwd + bwd" + (" + NCCL all-reduce" if world > 1 else "") + ")")
-                           if use_graph else "eager render() + autograd",
+                           if use_graph else (graph_note or "eager render() + autograd"),
                    "grad_collective": ("none" if world == 1 else ("nvls-multimem.red fused in preprocess_bwd" if symm is not None
                                                                  else "nccl all-reduce of the flat buffer")),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
@@ -624,8 +635,23 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         line.update(cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gout, dev))
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish(world, dev)
+
+
+def finish(world, dev):
+    """Multi-rank teardown.  With CUDA graphs that captured NCCL kernels still alive, dist.destroy_process_group()
+    never returned on the 2-GPU box (both ranks had printed their results; the launcher then waited for its 900 s
+    limit).  Nothing is left to clean up that the process exit does not release: meet once, flush, leave."""
+    if world == 1:
+        return
+    import torch.distributed as dist
+
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    torch.cuda.synchronize(dev)
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def cpu_and_parity(params, verts, faces, cams_host, pc, posed, cams_dev, bg, gout, dev):

@@ -112,8 +112,11 @@ def main():
     if rank == 0:
         out["ok"] = ok
         print(json.dumps(out), flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if ok else 1)
+    # no dist.destroy_process_group(): with graphs that captured NCCL kernels alive it never returned (see bench.finish)
+    torch.cuda.synchronize(dev)
+    dist.barrier()
+    sys.stdout.flush()
+    os._exit(0 if ok else 1)
 
 
 if __name__ == "__main__":
