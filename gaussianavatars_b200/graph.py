@@ -27,7 +27,7 @@ import torch
 from . import rasterizer as R
 from .renderer import render
 from .rasterizer import l1_loss_u8
-from .training import photometric_loss
+from .training import binding_regularizers, photometric_loss
 
 
 class _Pipe:
@@ -55,7 +55,7 @@ def camera_block(cam) -> torch.Tensor:
 class GraphedFrame:
     def __init__(self, pc, width: int, height: int, fovx: float, fovy: float, bg: torch.Tensor, loss: str = "l1_u8",
                  lambda_dssim: float = 0.2, host_inputs: bool = False, capacity: Optional[int] = None,
-                 headroom: float = 1.5, after_backward=None, warm_cameras=None):
+                 headroom: float = 1.5, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
         host_inputs: inputs handed to `set_inputs()` as (pinned) HOST tensors -- camera block, ground truth -- are
@@ -65,12 +65,17 @@ class GraphedFrame:
         140-byte camera copy at the head of the graph queued on the copy engine behind the 6 MB ground truth of the
         NEXT step and delayed every replay by the full 124 us of that transfer.)
         after_backward: optional callable run inside the capture after backward (e.g. the gradient all-reduce).
-        warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity."""
+        warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity.
+        regularizers: keyword arguments of `binding_regularizers` (threshold_xyz, lambda_scale, ...; {} = the
+        reference's defaults): the position / scale terms of train.py:134-146 are added to the loss inside the graph."""
         if loss not in ("l1_u8", "photometric", "dL_dimage"):
             raise ValueError("loss must be 'l1_u8', 'photometric' or 'dL_dimage'")
         self.pc, self.W, self.H, self.fovx, self.fovy = pc, int(width), int(height), float(fovx), float(fovy)
         self.loss_kind, self.lambda_dssim, self.host_inputs = loss, float(lambda_dssim), bool(host_inputs)
         self.after_backward = after_backward
+        self.regularizers = regularizers
+        if regularizers is not None and loss == "dL_dimage":
+            raise ValueError("regularizers need a scalar loss ('l1_u8' or 'photometric')")
         self.headroom = float(headroom)
         dev = pc._xyz.device
         self.device = dev
@@ -138,11 +143,12 @@ class GraphedFrame:
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
         img = out["render"]
-        if self.loss_kind == "l1_u8":
-            loss = l1_loss_u8(img, self.gt)
-            loss.backward()
-        elif self.loss_kind == "photometric":
-            loss = photometric_loss(img, self.gt, self.lambda_dssim)
+        if self.loss_kind in ("l1_u8", "photometric"):
+            loss = l1_loss_u8(img, self.gt) if self.loss_kind == "l1_u8" else photometric_loss(img, self.gt, self.lambda_dssim)
+            if self.regularizers is not None:
+                lx, ls = binding_regularizers(pc._xyz, pc._scaling, out["radii"], getattr(pc, "binding", None),
+                                              getattr(pc, "face_scaling", None), **self.regularizers)
+                loss = loss + lx + ls
             loss.backward()
         else:
             loss = None
