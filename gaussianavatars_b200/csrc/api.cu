@@ -316,7 +316,8 @@ int32_t gab200_counters_ok(const uint32_t* c, uint32_t frame_seq) {
   if (c == nullptr) return GAB200_ERR_INVALID_ARGUMENT;
   const volatile uint32_t* v = c;
   if (v[GAB200_CTR_SEQ] != frame_seq) return -1;
-  return (v[GAB200_CTR_BUCKET_OVERFLOW] == 0 && v[GAB200_CTR_NUM_RENDERED] <= v[GAB200_CTR_CAPACITY]) ? 1 : 0;
+  return (v[GAB200_CTR_NUM_RENDERED_HI] == 0 && v[GAB200_CTR_BUCKET_OVERFLOW] == 0 &&
+          v[GAB200_CTR_NUM_RENDERED] <= v[GAB200_CTR_CAPACITY]) ? 1 : 0;
 }
 
 const char* gab200_status_string(int32_t s) {
@@ -601,6 +602,7 @@ int64_t gab200_forward(const gab200_forward_args* a, gab200_frame_state* st, voi
     if (rc < 0) return rc;
     redo = true;
   }
+  if (f.ctr_host[GAB200_CTR_NUM_RENDERED_HI] != 0) return GAB200_ERR_OVERFLOW;  // > 2^32 - 1 instances
   const int64_t N = (int64_t)f.ctr_host[GAB200_CTR_NUM_RENDERED];
   st->depth_key_min = ~f.ctr_host[GAB200_CTR_NOT_MIN_DEPTH_KEY];
   st->depth_key_max = f.ctr_host[GAB200_CTR_MAX_DEPTH_KEY];

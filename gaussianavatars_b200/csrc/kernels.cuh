@@ -72,7 +72,10 @@ struct TileSpan {
 // ---- launchers (each counts its launches) ----
 // Per-splat depth sort as a bucket sort (binning.cu header): bookkeeping arrays in the geometry buffer.
 #define GAB_DEPTH_BUCKET_CAP 2048   // splats one bucket may hold before the frame falls back to the radix path
-#define GAB_DEPTH_META_WORDS GAB200_NUM_COUNTERS  // the frame counters of the public header (GAB200_CTR_*)
+// the frame counters of the public header (GAB200_CTR_*) + two private words: the 64-bit instance total
+// (meta[GAB_META_TOTAL64 .. +1], 8-byte aligned), from which GAB200_CTR_NUM_RENDERED_HI is published
+#define GAB_DEPTH_META_WORDS (GAB200_NUM_COUNTERS + 2)
+#define GAB_META_TOTAL64 GAB200_NUM_COUNTERS
 struct DepthBuckets {
   uint32_t* counts;     // [nb] splats per bucket           } zeroed together with meta before preprocess
   uint32_t* tiles;      // [nb] instances per bucket        }

@@ -49,11 +49,12 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     __syncthreads();
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  // the other 44 bytes per splat: positions / scales staged with 128-bit loads, quaternion as one float4
-  __shared__ float xyz_s[PRE_NT * 3], scale_s[PRE_NT * 3];
-  RawAttr raw;
-  load_raw_staged<PRE_NT>(a, i, xyz_s, scale_s, raw);
   if (i >= a.P) return;
+  // the other 44 bytes per splat: quaternion as one LDG.128, positions / scales / opacity as coalesced scalar loads
+  // (staging the two 12-byte-stride arrays through shared memory for 128-bit loads was built and measured:
+  // preprocess 31 -> 37 us, one more barrier for 24 of the 284 bytes -- load_raw_staged in splat_math.cuh)
+  RawAttr raw;
+  load_raw(a, i, raw);
   const float* my_sh = sh_s + threadIdx.x * sh_stride;
   const int W = a.image_width, H = a.image_height;
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
@@ -224,9 +225,13 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
     const unsigned live = __activemask();
     const uint32_t kmin = __reduce_min_sync(live, dkey);
     const uint32_t kmax = __reduce_max_sync(live, tiles_out ? dkey : 0u);
+    const uint32_t warp_tiles = __reduce_add_sync(live, tiles_out);  // <= 32 x (tiles of the image): fits 32 bits
     if ((threadIdx.x & 31) == (__ffs(live) - 1) && kmin != 0xffffffffu) {
       atomicMax(bk.meta + 0, ~kmin);
       atomicMax(bk.meta + 1, kmax);
+      // 64-bit instance total: the 32-bit emission offsets / tile ranges wrap silently beyond 2^32 - 1 instances,
+      // the host turns a non-zero high word into GAB200_ERR_OVERFLOW
+      atomicAdd(reinterpret_cast<unsigned long long*>(bk.meta + GAB_META_TOTAL64), (unsigned long long)warp_tiles);
     }
     if (bk.enabled && tiles_out) {
       const uint32_t b = depth_bucket(dkey, bk);
@@ -589,8 +594,10 @@ __global__ void publish_counters_kernel(uint32_t* __restrict__ counters, const u
   }
   counters[GAB200_CTR_CAPACITY] = capacity;
   counters[GAB200_CTR_SEQ] = seq;
+  const uint32_t hi = counters[GAB_META_TOTAL64 + 1];
+  counters[GAB200_CTR_NUM_RENDERED_HI] = hi;
   if (sticky_overflow != nullptr &&
-      (counters[GAB200_CTR_BUCKET_OVERFLOW] != 0 || counters[GAB200_CTR_NUM_RENDERED] > capacity))
+      (hi != 0 || counters[GAB200_CTR_BUCKET_OVERFLOW] != 0 || counters[GAB200_CTR_NUM_RENDERED] > capacity))
     *sticky_overflow = 1u;
 }
 void launch_publish_counters(uint32_t* counters, const uint32_t* offsets, int P, uint32_t capacity, uint32_t seq,

@@ -145,9 +145,9 @@ struct BindCtx {
 };
 
 // The 11 per-splat floats besides the SH coefficients (position, quaternion, scales, opacity; raw or activated
-// depending on the input mode).  The per-splat kernels fill it with 128-bit accesses: the quaternion is one float4
-// per thread, the two 12-byte-stride arrays (positions, scales) are staged through shared memory by stage_rows_in
-// (coalesced LDG.128, odd row stride), the 4-byte opacity is a coalesced scalar load.
+// depending on the input mode).  The quaternion is one float4 (LDG.128) per thread; positions and scales have a
+// 12-byte stride and are read as coalesced scalars by default (load_raw) -- load_raw_staged brings them in through
+// shared memory with LDG.128 instead and is kept as the measured alternative (slower at 100k splats: see preprocess.cu).
 struct RawAttr {
   float x[3], q[4], s[3], o;
 };

@@ -84,6 +84,8 @@ enum {
   GAB200_CTR_BUCKET_OVERFLOW = 4,   /* != 0: a depth bucket outgrew shared memory (depth_hint_* did not fit this frame) */
   GAB200_CTR_CAPACITY = 5,          /* capacity the binning stages ran with */
   GAB200_CTR_SEQ = 6,               /* caller's frame_seq echoed back: tells a finished copy from a stale one */
+  GAB200_CTR_NUM_RENDERED_HI = 7,   /* bits 32.. of the instance total: non-zero = more than 2^32 - 1 instances (the 32-bit
+                                       offsets wrapped: GAB200_ERR_OVERFLOW) */
   GAB200_NUM_COUNTERS = 8
 };
 
