@@ -40,7 +40,7 @@ class ForwardArgs(C.Structure):
         ("colors_precomp", C.c_void_p),
         ("binding", C.c_void_p), ("num_faces", C.c_int32), ("face_center", C.c_void_p),
         ("face_orien_mat", C.c_void_p), ("face_scaling", C.c_void_p),
-        ("out_color", C.c_void_p), ("radii", C.c_void_p),
+        ("out_color", C.c_void_p), ("radii", C.c_void_p), ("visibility", C.c_void_p),
         ("alloc_geom", ALLOC_FN), ("alloc_binning", ALLOC_FN), ("alloc_image", ALLOC_FN), ("alloc_user", C.c_void_p),
     ]
 

@@ -385,7 +385,9 @@ int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capaci
     StageScope sc(GAB200_STAGE_SCAN, stream);
     if (bucket) {
       // per-splat depth order + emission offsets as a bucket sort over the hinted key range -- see binning.cu
-      launch_depth_bucket_sort(f.P, g.buckets, g.depth_keys[0], g.tiles_touched, g.depth_keys[1], g.ids[1], g.offsets, stream);
+      launch_depth_bucket_sort(f.P, g.buckets, g.depth_keys[0], g.tiles_touched, g.depth_keys[1], g.ids[1], g.offsets,
+                               capacity, a->frame_seq, a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr,
+                               stream);
       f.selA = 1;
       f.order_count = g.buckets.meta + GAB200_CTR_NUM_LISTED;
     } else {
@@ -396,8 +398,9 @@ int enqueue_geometry(Frame& f, bool bucket, bool run_preprocess, uint32_t capaci
         GAB_CUDA(run_scan(g.scan_temp, g.scan_temp_bytes, g.ids[f.selA], g.tiles_touched, g.offsets, f.P, stream));
       f.order_count = nullptr;
     }
-    launch_publish_counters(g.buckets.meta, (bucket || f.counting) ? nullptr : g.offsets, bucket ? 0 : f.P, capacity,
-                            a->frame_seq, a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr, stream);
+    if (!bucket)
+      launch_publish_counters(g.buckets.meta, f.counting ? nullptr : g.offsets, f.P, capacity, a->frame_seq,
+                              a->sync_mode == GAB200_SYNC_NONE ? a->overflow_flag : nullptr, stream);
   }
   GAB_STAGE_CHECK(f.dbg, stream);
   GAB_CUDA(cudaMemcpyAsync(f.ctr_host, g.buckets.meta, sizeof(uint32_t) * GAB200_NUM_COUNTERS, cudaMemcpyDeviceToHost,

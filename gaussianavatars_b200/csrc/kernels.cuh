@@ -101,9 +101,11 @@ void launch_preprocess(const gab200_forward_args& a, SplatRec* rec, SplatAux* au
                        uint8_t* clamped, uint32_t* depth_keys, uint32_t* ids, const DepthBuckets& buckets,
                        uint32_t* tile_count, cudaStream_t stream);
 // depth_keys [P] (by splat) -> sorted_ids [M] in (key, id) order and offsets [M] = inclusive instance counts
+// also publishes the frame counters (capacity, seq, overflow) of the bucket-sorted frame
 void launch_depth_bucket_sort(int P, const DepthBuckets& buckets, const uint32_t* depth_keys,
                               const uint32_t* tiles_touched, uint32_t* scratch_keys, uint32_t* sorted_ids,
-                              uint32_t* offsets, cudaStream_t stream);
+                              uint32_t* offsets, uint32_t capacity, uint32_t seq, uint32_t* sticky_overflow,
+                              cudaStream_t stream);
 void launch_bind_activate(const gab200_forward_args& a, float* means3D, float* opacities, float* scales, float* cov3D,
                           cudaStream_t stream);
 void launch_mark_visible(int P, const float* means3D, const float* V, uint8_t* present, cudaStream_t stream);

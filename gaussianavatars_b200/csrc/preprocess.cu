@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(PRE_NT) preprocess_kernel(gab200_forward_args 
   ax.depth = depth_out; ax.radius = radius_out; ax.tiles = tiles_out; ax.pad = 0;
   aux[i] = ax;
   a.radii[i] = radius_out;
+  if (a.visibility != nullptr) a.visibility[i] = radius_out > 0 ? 1 : 0;
   tiles_touched[i] = tiles_out;
   if (clamped != nullptr) clamped[i] = clamp_bits;
 }
@@ -310,7 +311,8 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* s, int n, uin
 __global__ void __launch_bounds__(DS_NT) depth_scatter_kernel(int P, DepthBuckets bk,
                                                               const uint32_t* __restrict__ depth_keys,
                                                               uint32_t* __restrict__ out_keys,
-                                                              uint32_t* __restrict__ out_ids) {
+                                                              uint32_t* __restrict__ out_ids, uint32_t capacity,
+                                                              uint32_t seq, uint32_t* __restrict__ sticky_overflow) {
   extern __shared__ uint32_t s_start[];  // [nb]
   __shared__ uint32_t warp_tot[DS_NT / 32];
   __shared__ uint32_t s_flag;
@@ -343,10 +345,15 @@ __global__ void __launch_bounds__(DS_NT) depth_scatter_kernel(int P, DepthBucket
     __syncthreads();
     const uint32_t N = block_exclusive_scan(s_start, nb, warp_tot);
     for (int b = tid; b < nb; b += DS_NT) bk.tile_base[b] = s_start[b];
-    if (tid == 0) {
-      bk.meta[2] = N;
-      bk.meta[3] = M;
-      bk.meta[4] = s_flag;
+    if (tid == 0) {  // the frame counters of a bucket-sorted frame (publish_counters_kernel does this on the radix path)
+      bk.meta[GAB200_CTR_NUM_RENDERED] = N;
+      bk.meta[GAB200_CTR_NUM_LISTED] = M;
+      bk.meta[GAB200_CTR_BUCKET_OVERFLOW] = s_flag;
+      bk.meta[GAB200_CTR_CAPACITY] = capacity;
+      bk.meta[GAB200_CTR_SEQ] = seq;
+      const uint32_t hi = bk.meta[GAB_META_TOTAL64 + 1];
+      bk.meta[GAB200_CTR_NUM_RENDERED_HI] = hi;
+      if (sticky_overflow != nullptr && (hi != 0 || s_flag != 0 || N > capacity)) *sticky_overflow = 1u;
     }
   }
 }
@@ -399,10 +406,11 @@ __global__ void __launch_bounds__(DB_NT) depth_bucket_kernel(DepthBuckets bk, co
 }
 
 void launch_depth_bucket_sort(int P, const DepthBuckets& bk, const uint32_t* depth_keys, const uint32_t* tiles_touched,
-                              uint32_t* scratch_keys, uint32_t* sorted_ids, uint32_t* offsets, cudaStream_t stream) {
+                              uint32_t* scratch_keys, uint32_t* sorted_ids, uint32_t* offsets, uint32_t capacity,
+                              uint32_t seq, uint32_t* sticky_overflow, cudaStream_t stream) {
   if (P <= 0) return;
-  depth_scatter_kernel<<<(P + DS_NT - 1) / DS_NT, DS_NT, bk.nb * sizeof(uint32_t), stream>>>(P, bk, depth_keys,
-                                                                                              scratch_keys, sorted_ids);
+  depth_scatter_kernel<<<(P + DS_NT - 1) / DS_NT, DS_NT, bk.nb * sizeof(uint32_t), stream>>>(
+      P, bk, depth_keys, scratch_keys, sorted_ids, capacity, seq, sticky_overflow);
   count_launch();
   depth_bucket_kernel<<<bk.nb, DB_NT, 0, stream>>>(bk, scratch_keys, sorted_ids, tiles_touched, offsets);
   count_launch();

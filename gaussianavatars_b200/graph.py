@@ -55,7 +55,7 @@ def camera_block(cam) -> torch.Tensor:
 class GraphedFrame:
     def __init__(self, pc, width: int, height: int, fovx: float, fovy: float, bg: torch.Tensor, loss: str = "l1_u8",
                  lambda_dssim: float = 0.2, host_inputs: bool = False, capacity: Optional[int] = None,
-                 headroom: float = 1.5, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None):
+                 headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
         host_inputs: inputs handed to `set_inputs()` as (pinned) HOST tensors -- camera block, ground truth -- are

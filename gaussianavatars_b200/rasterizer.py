@@ -13,6 +13,7 @@ backward returns gradients for the raw parameters and for face_center / face_ori
 from __future__ import annotations
 
 import ctypes as C
+import threading
 from typing import NamedTuple, Optional
 
 import torch
@@ -196,6 +197,14 @@ class CaptureSlot:
 
 
 _capture_slot = None
+_tls = threading.local()
+
+
+def visible_of(radii: torch.Tensor):
+    """The `radii > 0` mask the forward that produced `radii` wrote beside it (None if that was not the last forward
+    of this thread)."""
+    v = getattr(_tls, "visible", None)
+    return v[1] if v is not None and v[0] == radii.data_ptr() else None
 
 
 def _run_forward(a: N.ForwardArgs, device, need_backward: bool, hints: Optional[FrameHints] = None):
@@ -203,7 +212,9 @@ def _run_forward(a: N.ForwardArgs, device, need_backward: bool, hints: Optional[
     H, W, P = a.image_height, a.image_width, a.P
     color = torch.empty((3, H, W), dtype=torch.float32, device=device)
     radii = torch.empty((P,), dtype=torch.int32, device=device)
-    a.out_color, a.radii = color.data_ptr(), radii.data_ptr()
+    visible = torch.empty((P,), dtype=torch.bool, device=device)   # radii > 0, written by the preprocess kernel
+    a.out_color, a.radii, a.visibility = color.data_ptr(), radii.data_ptr(), visible.data_ptr()
+    _tls.visible = (radii.data_ptr(), visible)   # renderer.py hands it out as `visibility_filter`
     cb, holder = N.begin_forward(device, need_backward)
     a.alloc_geom = a.alloc_binning = a.alloc_image = cb
     st = N.FrameState()

@@ -17,7 +17,7 @@ import math
 
 import torch
 
-from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, hints_of, rasterize_bound
+from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer, hints_of, rasterize_bound, visible_of
 
 
 def _camera_block(cam, device):
@@ -62,8 +62,14 @@ def render_bound(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, ove
     rendered_image, radii = rasterize_bound(rs, pc._xyz, pc._rotation, pc._scaling, pc._opacity, pc._features_dc,
                                             pc._features_rest, binding, fc, fR, fs, means2D=screenspace_points,
                                             colors_precomp=override_color, grad_sink=pc)
-    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": _visible(radii),
             "radii": radii}
+
+
+def _visible(radii):
+    """`radii > 0` (gaussian_renderer/__init__.py:100): the forward wrote it next to the radii (one byte per splat)."""
+    v = visible_of(radii)
+    return v if v is not None else radii > 0
 
 
 def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_color=None, fused=None):
@@ -105,5 +111,5 @@ def render(viewpoint_camera, pc, pipe, bg_color, scaling_modifier=1.0, override_
     rendered_image, radii = rasterizer(means3D=means3D, means2D=means2D, shs=shs, colors_precomp=colors_precomp,
                                        opacities=opacity, scales=scales, rotations=rotations,
                                        cov3D_precomp=cov3D_precomp)
-    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": radii > 0,
+    return {"render": rendered_image, "viewspace_points": screenspace_points, "visibility_filter": _visible(radii),
             "radii": radii}

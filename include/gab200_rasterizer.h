@@ -153,6 +153,8 @@ typedef struct gab200_forward_args {
   /* outputs */
   float* out_color;   /* [3,H,W] */
   int32_t* radii;     /* [P] */
+  uint8_t* visibility; /* [P] or NULL: radii > 0 as bytes -- render()'s `visibility_filter`
+                          (gaussian_renderer/__init__.py:100) without a separate compare kernel */
 
   /* scratch (the reference's geomBuffer / binningBuffer / imgBuffer) */
   gab200_alloc_fn alloc_geom, alloc_binning, alloc_image;
