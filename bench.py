@@ -450,23 +450,26 @@ def main():
             f_ = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="l1_u8", host_inputs=True,
                               warm_cameras=cam_host_blocks,
                               after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
-            f_.set_inputs(camera=cam_host_blocks[0], verts=posed[0].detach(), gt_u8=gt_pin[k])
-            f_.capture()
+            f_.gt_stage.copy_(gt_host[k])   # the loader's job: decoded frames land in the two pinned staging buffers
+            f_.cam_stage.copy_(cam_host_blocks[0])
+            f_.set_inputs(verts=posed[0].detach())
+            f_.upload_staged()
             e2e_frames.append(f_)
+        e2e_frames[0].prefetch_for(e2e_frames[1])
+        e2e_frames[1].prefetch_for(e2e_frames[0])
+        for f_ in e2e_frames:
+            f_.capture()
         done = [torch.cuda.Event() for _ in range(2)]
-        # the first step's inputs are on their way before the clock starts
-        e2e_frames[0].set_inputs(camera=cam_host_blocks[0], gt_u8=gt_pin[0])
 
         def step_e2e(i):
-            f_ = e2e_frames[i % 2]
+            f_, nxt = e2e_frames[i % 2], e2e_frames[(i + 1) % 2]
+            # the NEXT step's camera block goes into the other frame's pinned staging (140 bytes; its ground truth is
+            # already in that frame's pinned staging buffer): this step's graph uploads both on a forked branch while
+            # it computes.  The last reader of that staging was graph i-2, finished (we waited for done[i-2]).
+            nxt.cam_stage.copy_(cam_host_blocks[(i + 1) % len(cam_host_blocks)])
             f_.set_inputs(verts=posed[i % len(posed)].detach())
-            f_.run()                                                        # waits (on the GPU) for this step's uploads
+            f_.run()
             done[i % 2].record()
-            # the NEXT step's camera block and ground truth: uploaded from pinned memory on the other frame's copy
-            # stream while this step computes (a two-deep loader); the uploads wait for that frame's previous replay
-            # to have read its buffers
-            e2e_frames[(i + 1) % 2].set_inputs(camera=cam_host_blocks[(i + 1) % len(cam_host_blocks)],
-                                               gt_u8=gt_pin[(i + 1) % 2])
             if i > 0:  # read the PREVIOUS step's loss: every step's result reaches the host inside the timed region
                 done[(i - 1) % 2].synchronize()
                 losses.append(float(e2e_frames[(i - 1) % 2].loss_host))
@@ -511,7 +514,10 @@ def main():
             loss_ready[last % 2].synchronize()
             losses.append(float(loss_host[last % 2]))
 
-    for i in range(3):
+    if use_graph:   # step 0's own inputs (every later step's arrive through the previous step's graph)
+        e2e_frames[0].cam_stage.copy_(cam_host_blocks[0])
+        e2e_frames[0].upload_staged()
+    for i in range(4):
         step_e2e(i)
     barrier()
     losses.clear()
@@ -613,7 +619,8 @@ def main():
                   "what": "same step through the eager render() + autograd (sync mode LATE), L2 flushed"},
         "e2e": {"value": world * K / (ms_e2e / 1e3), "unit": "frames/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
-                "path": "GraphedFrame(host_inputs=True, loss='l1_u8')" if use_graph else "eager render() + l1_loss_u8"},
+                "path": ("two GraphedFrame(host_inputs=True, loss='l1_u8') prefetching each other's inputs from pinned "
+                         "staging inside their graphs") if use_graph else "eager render() + l1_loss_u8"},
         "gpu_launches": int(launches),
         "graph_overflow": bool(overflow_steps),
         "clocks": clk.summary(),

@@ -132,7 +132,7 @@ PHOTOMETRIC_SCRATCH_HEAD = 4
 EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", "gab200_bind_activate",
                     "gab200_export_binning", "gab200_launch_count", "gab200_status_string", "gab200_abi_version",
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
-                    "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8",
+                    "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8", "gab200_l1_loss_u8_backward",
                     "gab200_photometric_loss", "gab200_adam_step", "gab200_tune", "gab200_counters_ok",
                     "gab200_regularize_forward", "gab200_regularize_backward", "gab200_densify_scratch_bytes", "gab200_densify_plan", "gab200_densify_apply")
 
@@ -192,6 +192,8 @@ def lib():
         L.gab200_counters_ok.argtypes = [C.c_void_p, C.c_uint32]
         L.gab200_l1_loss_u8.restype = C.c_int32
         L.gab200_l1_loss_u8.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.gab200_l1_loss_u8_backward.restype = C.c_int32
+        L.gab200_l1_loss_u8_backward.argtypes = [C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.gab200_photometric_loss.restype = C.c_int32
         L.gab200_photometric_loss.argtypes = [C.POINTER(PhotometricArgs), C.c_void_p]
         L.gab200_adam_step.restype = C.c_int32

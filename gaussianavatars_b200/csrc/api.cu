@@ -733,10 +733,18 @@ int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, con
 
 int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (n < 0 || !loss || (n > 0 && (!img || !gt || !grad))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (n < 0 || !loss || (n > 0 && (!img || !gt))) return GAB200_ERR_INVALID_ARGUMENT;
   if (check_arch() < 0) return GAB200_ERR_ARCH;
   GAB_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), stream));
-  launch_l1_loss_u8(n, img, gt, grad, loss, stream);
+  launch_l1_loss_u8(n, img, gt, nullptr, grad, loss, stream);
+  return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
+}
+
+int32_t gab200_l1_loss_u8_backward(int64_t n, const float* img, const uint8_t* gt, const float* upstream, float* grad,
+                                   void* stream_) {
+  if (n < 0 || (n > 0 && (!img || !gt || !grad))) return GAB200_ERR_INVALID_ARGUMENT;
+  if (check_arch() < 0) return GAB200_ERR_ARCH;
+  launch_l1_loss_u8(n, img, gt, upstream, grad, nullptr, (cudaStream_t)stream_);
   return cudaPeekAtLastError() == cudaSuccess ? GAB200_OK : GAB200_ERR_CUDA;
 }
 

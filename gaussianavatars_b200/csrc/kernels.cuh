@@ -165,7 +165,8 @@ void launch_face_frame_backward(int F, const float* verts, const int32_t* faces,
                                 const float* g_fs, float* g_verts, cudaStream_t stream);
 
 // loss.cu
-void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, cudaStream_t stream);
+void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, const float* upstream, float* grad, float* loss,
+                       cudaStream_t stream);
 
 void launch_photometric_loss(int C, int H, int W, const float* img, const void* gt, int gt_is_u8, float lambda,
                              float* grad, float* loss, float* scratch, cudaStream_t stream);

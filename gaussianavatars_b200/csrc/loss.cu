@@ -9,11 +9,16 @@
 namespace gab {
 
 // VEC: img/grad 16-B aligned and gt 4-B aligned (checked by the launcher); otherwise every thread takes the scalar loop.
+// grad == nullptr: loss only.  loss_sum == nullptr: gradient only.  upstream (device scalar, may be NULL = 1) scales the
+// gradient: the backward of `loss = l1(img, gt)` under autograd is this kernel with loss_sum == nullptr, so no separate
+// multiply pass over the (3,H,W) gradient is needed.
 template <bool VEC>
 __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float* __restrict__ img,
-                                                         const uint8_t* __restrict__ gt, float inv_n,
+                                                         const uint8_t* __restrict__ gt, float inv_n_,
+                                                         const float* __restrict__ upstream,
                                                          float* __restrict__ grad, float* __restrict__ loss_sum) {
   const int64_t i4 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  const float inv_n = upstream != nullptr ? inv_n_ * __ldg(upstream) : inv_n_;
   float acc = 0.f;
   if (VEC && i4 + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(img + i4);
@@ -22,14 +27,16 @@ __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float*
     const float d2 = v.z - __fdiv_rn((float)g.z, 255.f), d3 = v.w - __fdiv_rn((float)g.w, 255.f);
     acc = fabsf(d0) + fabsf(d1) + fabsf(d2) + fabsf(d3);
     auto sgn = [](float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); };
-    *reinterpret_cast<float4*>(grad + i4) = make_float4(sgn(d0) * inv_n, sgn(d1) * inv_n, sgn(d2) * inv_n, sgn(d3) * inv_n);
+    if (grad != nullptr)
+      *reinterpret_cast<float4*>(grad + i4) = make_float4(sgn(d0) * inv_n, sgn(d1) * inv_n, sgn(d2) * inv_n, sgn(d3) * inv_n);
   } else {
     for (int64_t i = i4; i < n && i < i4 + 4; i++) {
       const float d = img[i] - __fdiv_rn((float)gt[i], 255.f);
       acc += fabsf(d);
-      grad[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
+      if (grad != nullptr) grad[i] = (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f)) * inv_n;
     }
   }
+  if (loss_sum == nullptr) return;  // gradient-only launch (uniform: no barrier is skipped by part of a block)
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, m);
   __shared__ float part[8];
@@ -39,19 +46,20 @@ __global__ void __launch_bounds__(256) l1_loss_u8_kernel(int64_t n, const float*
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; w++) s += part[w];
-    atomicAdd(loss_sum, s * inv_n);
+    atomicAdd(loss_sum, s * inv_n_);
   }
 }
 
-void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, cudaStream_t stream) {
+void launch_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, const float* upstream, float* grad, float* loss,
+                       cudaStream_t stream) {
   if (n == 0) return;
   const int64_t threads = (n + 3) / 4;
   const bool aligned = (((uintptr_t)img | (uintptr_t)grad) & 15) == 0 && ((uintptr_t)gt & 3) == 0;
   const unsigned blocks = (unsigned)((threads + 255) / 256);
   if (aligned)
-    l1_loss_u8_kernel<true><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, grad, loss);
+    l1_loss_u8_kernel<true><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, upstream, grad, loss);
   else  // a contiguous view with a storage offset (batch[b], a uint8 slice): same result through scalar accesses
-    l1_loss_u8_kernel<false><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, grad, loss);
+    l1_loss_u8_kernel<false><<<blocks, 256, 0, stream>>>(n, img, gt, 1.0f / (float)n, upstream, grad, loss);
   count_launch();
 }
 

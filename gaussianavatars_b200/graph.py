@@ -58,12 +58,16 @@ class GraphedFrame:
                  headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
-        host_inputs: inputs handed to `set_inputs()` as (pinned) HOST tensors -- camera block, ground truth -- are
-        uploaded on this frame's own copy stream, where they may run under whatever the main stream is doing (e.g. the
-        previous step, with two frames used alternately); `run()` makes the replay wait for them ON THE GPU, and the
-        graph ends with a D2H copy of the loss to `loss_host`.  (No H2D node sits inside the graph: measured, a
-        140-byte camera copy at the head of the graph queued on the copy engine behind the 6 MB ground truth of the
-        NEXT step and delayed every replay by the full 124 us of that transfer.)
+        host_inputs: the frame owns pinned STAGING tensors (`cam_stage` (35,) float32, `gt_stage` (3,H,W) uint8) that a
+        loader fills, and the graph ends with a D2H copy of the loss to `loss_host`.  How the staged inputs reach the
+        device: (a) `set_inputs()` with HOST tensors uploads them on this frame's copy stream and `run()` makes the
+        replay wait for them on the GPU; or (b) two frames used alternately prefetch for each other INSIDE their graphs
+        (`a.prefetch_for(b); b.prefetch_for(a)` before capture): a forked branch of a's graph copies b's staging
+        tensors into b's device buffers while a computes, so the upload of step i+1 runs under step i with no event
+        between graphs.  (An H2D node at the HEAD of the consuming graph is what does not work: measured, a 140-byte
+        camera copy queued on the copy engine behind the 6 MB ground truth of the next step and delayed every replay
+        by the full 124 us of that transfer; and ordering uploads against replays with cross-stream events costs
+        ~40 us per step, profiles/r02/e2e_loop_probe.json.)
         after_backward: optional callable run inside the capture after backward (e.g. the gradient all-reduce).
         warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity.
         regularizers: keyword arguments of `binding_regularizers` (threshold_xyz, lambda_scale, ...; {} = the
@@ -86,6 +90,10 @@ class GraphedFrame:
         self.gt = torch.zeros((3, self.H, self.W), dtype=torch.uint8, device=dev) if loss != "dL_dimage" else None
         self.dL_dimage = torch.zeros((3, self.H, self.W), dtype=torch.float32, device=dev) if loss == "dL_dimage" else None
         self.cam_host = torch.zeros(35, dtype=torch.float32).pin_memory() if host_inputs else None  # staging
+        self.cam_stage = self.cam_host
+        self.gt_stage = (torch.zeros((3, self.H, self.W), dtype=torch.uint8).pin_memory()
+                         if host_inputs and self.gt is not None else None)
+        self._prefetch_target = None
         self._gt_ready = self._done = None   # events ordering the ground-truth upload against the replays
         self.loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
         self.loss = None
@@ -122,6 +130,20 @@ class GraphedFrame:
         if dL_dimage is not None:
             self.dL_dimage.copy_(dL_dimage, non_blocking=True)
 
+    def prefetch_for(self, other: "GraphedFrame"):
+        """This frame's graph will, on a forked branch, copy `other`'s pinned staging tensors (cam_stage, gt_stage)
+        into `other`'s device inputs while it computes.  Call before capture()."""
+        if not (self.host_inputs and other.host_inputs):
+            raise ValueError("prefetching needs host_inputs=True on both frames")
+        self._prefetch_target = other
+        return self
+
+    def upload_staged(self):
+        """Eager upload of this frame's own staging tensors (the first step of a prefetching pair)."""
+        self.cam.copy_(self.cam_stage, non_blocking=True)
+        if self.gt_stage is not None:
+            self.gt.copy_(self.gt_stage, non_blocking=True)
+
     def _upload(self, dst, src_host):
         """H2D on the copy stream: after the last replay that read `dst`, concurrently with the main stream."""
         if self._done is not None:
@@ -140,6 +162,14 @@ class GraphedFrame:
         for p in self._params():
             p.grad = None
         self.verts.grad = None
+        other = self._prefetch_target
+        if other is not None:   # forked branch: the other frame's next inputs travel while this frame computes
+            cur = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(cur)
+            with torch.cuda.stream(self._side):
+                other.cam.copy_(other.cam_stage, non_blocking=True)
+                if other.gt_stage is not None:
+                    other.gt.copy_(other.gt_stage, non_blocking=True)
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
         img = out["render"]
@@ -158,6 +188,8 @@ class GraphedFrame:
         if loss is not None:
             self.loss = loss.detach()
             self.loss_host.copy_(self.loss, non_blocking=True)
+        if other is not None:   # join the branch (a captured fork must end inside the graph)
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.image, self.radii, self.viewspace_points = img.detach(), out["radii"], out["viewspace_points"]
 
     # ---- capture ---------------------------------------------------------------------------------------------------

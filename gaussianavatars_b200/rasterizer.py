@@ -609,19 +609,25 @@ class _L1LossU8(torch.autograd.Function):
         if gt_u8.dtype != torch.uint8 or gt_u8.numel() != img.numel():
             raise TypeError("gt must be a uint8 tensor with the image's number of elements")
         gt = gt_u8 if gt_u8.is_contiguous() else gt_u8.contiguous()
-        grad = torch.empty_like(img)
         loss = torch.empty((), dtype=torch.float32, device=device)
         with torch.cuda.device(device):
             stream = torch.cuda.current_stream(device).cuda_stream
-            N.check(N.lib().gab200_l1_loss_u8(img.numel(), img.data_ptr(), gt.data_ptr(), grad.data_ptr(),
-                                              loss.data_ptr(), C.c_void_p(stream)), "gab200_l1_loss_u8")
-        ctx.save_for_backward(grad)
+            N.check(N.lib().gab200_l1_loss_u8(img.numel(), img.data_ptr(), gt.data_ptr(), None, loss.data_ptr(),
+                                              C.c_void_p(stream)), "gab200_l1_loss_u8")
+        ctx.save_for_backward(img, gt)
         return loss
 
     @staticmethod
     def backward(ctx, g):
-        (grad,) = ctx.saved_tensors
-        return grad.mul_(g), None  # in place: the buffer is ours and single-use
+        img, gt = ctx.saved_tensors
+        device = img.device
+        grad = torch.empty_like(img)
+        gs = g if (g.dtype == torch.float32 and g.device == device) else g.to(device=device, dtype=torch.float32)
+        with torch.cuda.device(device):
+            stream = torch.cuda.current_stream(device).cuda_stream
+            N.check(N.lib().gab200_l1_loss_u8_backward(img.numel(), img.data_ptr(), gt.data_ptr(), gs.data_ptr(),
+                                                       grad.data_ptr(), C.c_void_p(stream)), "gab200_l1_loss_u8_backward")
+        return grad, None
 
 
 def l1_loss_u8(image: torch.Tensor, gt_u8: torch.Tensor) -> torch.Tensor:

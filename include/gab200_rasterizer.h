@@ -269,8 +269,13 @@ int32_t gab200_face_frame_backward(int32_t F, int32_t V, const float* verts, con
 /* Mean absolute error between a rendered image (n = 3*H*W floats) and a uint8 ground truth (value/255), with its
  * gradient, in one pass: *loss = mean |img - gt/255|, grad[i] = sign(img[i] - gt[i]/255) / n.  `loss` is zeroed by the
  * library.  Replaces `l1_loss(image, gt_image)` + its autograd and the float32 upload of the ground truth
- * (utils/loss_utils.py:17-18, train.py:128-131); img/grad must be 16-byte aligned, gt 4-byte aligned. */
+ * (utils/loss_utils.py:17-18, train.py:128-131).  grad may be NULL (loss only). */
 int32_t gab200_l1_loss_u8(int64_t n, const float* img, const uint8_t* gt, float* grad, float* loss, void* stream);
+/* The gradient alone, scaled by an upstream gradient read from device memory (NULL = 1): grad[i] = *upstream *
+ * sign(img[i] - gt[i]/255) / n.  What autograd's backward of the loss calls (grad may be NULL in the forward above:
+ * loss only), so that no separate multiply pass runs over the (3,H,W) gradient. */
+int32_t gab200_l1_loss_u8_backward(int64_t n, const float* img, const uint8_t* gt, const float* upstream, float* grad,
+                                   void* stream);
 
 /* Photometric training loss of the reference with its gradient, in two launches:
  *   total = (1 - lambda_dssim) * mean|img - gt| + lambda_dssim * (1 - mean SSIM(img, gt))

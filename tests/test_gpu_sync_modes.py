@@ -174,3 +174,52 @@ def test_graphed_frame_detects_overflow_and_regrows():
     assert fr.captures == 2 and not fr.overflowed(wait=True)
     assert torch.equal(fr.image, img_ref)
     _grads_close([p.grad for p in pc.parameters()] + [fr.verts.grad, fr.viewspace_points.grad], g_ref)
+
+
+def test_two_frames_prefetching_each_others_host_inputs_inside_their_graphs():
+    """The e2e loader pattern of bench.py: frame A's graph uploads frame B's staged camera + ground truth on a forked
+    branch while it computes, and vice versa.  Every step must equal the eager step on the same inputs."""
+    import gaussianavatars_b200 as g
+    from gaussianavatars_b200 import synthetic as syn
+    from gaussianavatars_b200.graph import GraphedFrame, camera_block
+    from gaussianavatars_b200.renderer import render
+
+    dev = torch.device("cuda:0")
+    sc = h.avatar_scene(P=10_000, W=320, H=240, seed=9)
+    cams = [syn.orbit_camera(sc["W"], sc["H"], r=1.0, fovy_deg=20.0, azimuth_deg=a) for a in (-20.0, 5.0, 30.0)]
+    gen = torch.Generator().manual_seed(11)
+    gts = [torch.randint(0, 256, (3, sc["H"], sc["W"]), generator=gen, dtype=torch.uint8) for _ in range(3)]
+    pc = _model(sc, dev)
+    frames = []
+    for k in range(2):
+        f = GraphedFrame(pc, sc["W"], sc["H"], cams[0].FoVx, cams[0].FoVy, sc["bg"], loss="l1_u8", host_inputs=True,
+                         warm_cameras=[camera_block(c) for c in cams])
+        f.cam_stage.copy_(camera_block(cams[0]))
+        f.gt_stage.copy_(gts[0])
+        f.set_inputs(verts=sc["verts"].to(dev))
+        f.upload_staged()
+        frames.append(f)
+    frames[0].prefetch_for(frames[1])
+    frames[1].prefetch_for(frames[0])
+    for f in frames:
+        f.capture()
+    pc_e = _model(sc, dev)
+    frames[0].cam_stage.copy_(camera_block(cams[0]))
+    frames[0].gt_stage.copy_(gts[0])
+    frames[0].upload_staged()
+    for i in range(5):
+        cur, nxt = frames[i % 2], frames[(i + 1) % 2]
+        torch.cuda.synchronize()                       # the loader may only refill a staging buffer nobody is reading
+        nxt.cam_stage.copy_(camera_block(cams[(i + 1) % 3]))
+        nxt.gt_stage.copy_(gts[(i + 1) % 3])
+        cur.run(check=True)
+        torch.cuda.synchronize()
+        for p in pc_e.parameters():
+            p.grad = None
+        pc_e.update_mesh_properties(sc["verts"].to(dev))
+        out = render(cams[i % 3].to(dev), pc_e, Pipe, sc["bg"].to(dev))
+        loss = g.l1_loss_u8(out["render"], gts[i % 3].to(dev))
+        loss.backward()
+        assert torch.equal(cur.image, out["render"].detach()), f"step {i}: image differs"
+        assert abs(float(cur.loss_host) - float(loss)) <= 1e-6
+        _grads_close([p.grad for p in pc.parameters()], [p.grad for p in pc_e.parameters()])
