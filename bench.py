@@ -70,11 +70,13 @@ def parse():
     ap.add_argument("--exact-binning", action="store_true", help="emit the reference's full instance list")
     # other BASELINE.json configs (parity/scale cases, not the headline line): e.g. config 4 =
     #   --gpus 8 --splats 500000 --width 2048 --height 2048 --cameras 64
-    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "nvls"],
-                    help="N>1 gradient reduction: one NCCL all-reduce after backward, or fused into the backward kernel "
-                         "through NVLS multicast (multimem.red).  auto = nccl: measured on 2/4/8 B200s the push-style "
-                         "multicast reduction ties at N=2/4 and loses at N=8 (every replica receives N x the buffer), "
-                         "see DESIGN.md section 6")
+    ap.add_argument("--collective", default="auto", choices=["auto", "nccl", "nvls", "nvls2"],
+                    help="N>1 gradient reduction.  nccl: one ncclAllReduce after backward.  nvls2: this library's two-shot "
+                         "NVLS all-reduce kernel (multimem.ld_reduce + multimem.st, csrc/nvls.cu) on the symmetric-memory "
+                         "gradient buffer, captured inside the step's graph.  nvls: push-style multimem.red fused into "
+                         "preprocess_bwd (eager only; loses at N=8, every replica receives N x the buffer).  auto = "
+                         "nvls2 when the fabric has multicast and its self-test passes on every rank, else nccl "
+                         "(DESIGN.md section 6)")
     ap.add_argument("--splats", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -302,15 +304,25 @@ def main():
     verts, faces = syn.head_mesh()
     params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
     pc = MeshBoundGaussians(params, SH_DEGREE, verts, faces, pose_fn=syn.pose_mesh, device=dev, requires_grad=True)
-    symm = None
-    if world > 1 and args.collective == "nvls":
-        symm = gdist.SymmetricGradBuffer(pc)
-        if symm.enabled:
-            pc.symm_grad = symm
+    symm, collective_note = None, None
+    if world > 1 and args.collective != "nccl":
+        mode = "push" if args.collective == "nvls" else "two_shot"
+        why = None
+        try:
+            symm = gdist.SymmetricGradBuffer(pc, mode=mode)
+            ok = symm.enabled and (mode == "push" or symm.self_test())
+            if not ok:
+                why = getattr(symm, "error", "self-test of the two-shot kernel failed")
+        except Exception as e:
+            ok, why = False, f"{type(e).__name__}: {e}"
+        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag) == 0.0:
+            if args.collective != "auto":
+                raise RuntimeError(f"--collective {args.collective} unavailable: {why or 'another rank failed'}")
+            symm, collective_note = None, f"nvls2 unavailable ({why or 'another rank failed'}): nccl"
         else:
-            if args.collective == "nvls":
-                raise RuntimeError("NVLS multicast unavailable: " + getattr(symm, "error", "?"))
-            symm = None
+            pc.symm_grad = symm
     cams_host = make_cameras(N_CAMERAS)
     my_cams = [cams_host[i] for i in gdist.shard_frames(N_CAMERAS, rank, world)] or cams_host
     cams_dev = [c.to(dev) for c in my_cams]
@@ -395,22 +407,46 @@ def main():
 
     cam_blocks_dev = [camera_block(c) for c in cams_dev]
     c0 = my_cams[0]
-    use_graph = not args.no_graph and symm is None
+    use_graph = not args.no_graph and (symm is None or symm.mode == "two_shot")
     frame = None
     graph_note = None
-    if use_graph:
+
+    def hooks():
+        """(before_backward, after_backward) of the captured step for the collective in use."""
+        if world == 1:
+            return None, None
+        if symm is not None:
+            return symm.begin, symm.end
+        return None, (lambda: gdist.allreduce_splat_grads(pc))
+
+    def try_capture():
+        """The resident step as a graph; None (+ reason) if it cannot be captured.  Every rank must agree."""
+        fr, why = None, None
         try:
-            frame = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev,
-                                 after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
-            frame.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
-            frame.capture()
-        except Exception as e:  # e.g. a fabric on which NCCL cannot be captured: measure the eager step instead, and say so
-            frame, use_graph, graph_note = None, False, f"graph capture failed ({type(e).__name__}: {e}); eager step timed"
-        if world > 1:  # every rank must take the same path (a captured all-reduce cannot meet an eager one)
-            flag = torch.tensor([1.0 if use_graph else 0.0], device=dev)
+            before, after = hooks()
+            fr = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev,
+                              before_backward=before, after_backward=after)
+            fr.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
+            fr.capture()
+        except Exception as e:  # e.g. a fabric on which the collective cannot be captured
+            fr, why = None, f"{type(e).__name__}: {e}"
+        if world > 1:  # a captured collective cannot meet an eager one
+            flag = torch.tensor([1.0 if fr is not None else 0.0], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if float(flag) == 0.0 and use_graph:
-                frame, use_graph, graph_note = None, False, "another rank could not capture the step; eager step timed"
+            if float(flag) == 0.0:
+                fr, why = None, why or "another rank could not capture the step"
+        return fr, why
+
+    if use_graph:
+        frame, why = try_capture()
+        if frame is None and symm is not None and args.collective == "auto":
+            # the two-shot kernel + signal-pad barriers could not be captured here: NCCL inside the graph instead
+            collective_note = f"nvls2 not capturable ({why}): nccl"
+            symm = None
+            del pc.symm_grad
+            frame, why = try_capture()
+        if frame is None:
+            use_graph, graph_note = False, f"graph capture failed ({why}); eager step timed"
 
     def step_resident(i):
         if frame is None:
@@ -447,9 +483,9 @@ def main():
         # the other); camera block staged in pinned memory per step; loss scalar copied back by the graph, read late
         e2e_frames = []
         for k in range(2):
+            before_, after_ = hooks()
             f_ = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="l1_u8", host_inputs=True,
-                              warm_cameras=cam_host_blocks,
-                              after_backward=(lambda: gdist.allreduce_splat_grads(pc)) if world > 1 else None)
+                              warm_cameras=cam_host_blocks, before_backward=before_, after_backward=after_)
             f_.gt_stage.copy_(gt_host[k])   # the loader's job: decoded frames land in the two pinned staging buffers
             f_.cam_stage.copy_(cam_host_blocks[0])
             f_.set_inputs(verts=posed[0].detach())
@@ -609,10 +645,14 @@ def main():
         "config": {"workload": WORKLOAD, "splats": P_SPLATS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                    "faces": F, "instances_per_frame": int(n_inst), "binning": "exact" if args.exact_binning else "culled",
                    "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded dp{world}",
-                   "step": ("one CUDA-graph replay (face frame + fused fwd + bwd" + (" + NCCL all-reduce" if world > 1 else "") + ")")
+                   "step": ("one CUDA-graph replay (face frame + fused fwd + bwd" + (" + gradient all-reduce" if world > 1 else "") + ")")
                            if use_graph else (graph_note or "eager render() + autograd"),
-                   "grad_collective": ("none" if world == 1 else ("nvls-multimem.red fused in preprocess_bwd" if symm is not None
-                                                                 else "nccl all-reduce of the flat buffer")),
+                   "grad_collective": ("none" if world == 1 else
+                                       "nccl all-reduce of the flat buffer" if symm is None else
+                                       "nvls multimem.red fused in preprocess_bwd" if symm.mode == "push" else
+                                       "nvls two-shot all-reduce kernel (multimem.ld_reduce + multimem.st) on the "
+                                       "symmetric flat buffer, between two signal-pad barriers, inside the graph"),
+                   **({"collective_note": collective_note} if collective_note else {}),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
         "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},
         "eager": {"value": world * K / (ms_eager / 1e3), "unit": "frames/s", "ms_per_step": ms_eager / K,

@@ -134,7 +134,7 @@ EXPORTED_SYMBOLS = ("gab200_forward", "gab200_backward", "gab200_mark_visible", 
                     "gab200_stage_timing_enable", "gab200_stage_times", "gab200_face_frame_forward",
                     "gab200_face_frame_backward", "gab200_host_times", "gab200_l1_loss_u8", "gab200_l1_loss_u8_backward",
                     "gab200_photometric_loss", "gab200_adam_step", "gab200_tune", "gab200_counters_ok",
-                    "gab200_regularize_forward", "gab200_regularize_backward", "gab200_densify_scratch_bytes", "gab200_densify_plan", "gab200_densify_apply")
+                    "gab200_regularize_forward", "gab200_regularize_backward", "gab200_nvls_allreduce", "gab200_densify_scratch_bytes", "gab200_densify_plan", "gab200_densify_apply")
 
 _lib = None
 _lock = threading.Lock()
@@ -178,6 +178,8 @@ def lib():
         L.gab200_launch_count.restype = C.c_int64
         L.gab200_tune.restype = C.c_int32
         L.gab200_tune.argtypes = [C.c_int32, C.c_int32]
+        L.gab200_nvls_allreduce.restype = C.c_int32
+        L.gab200_nvls_allreduce.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p]
         L.gab200_regularize_forward.restype = C.c_int32
         L.gab200_regularize_forward.argtypes = [C.POINTER(RegularizeArgs), C.c_void_p]
         L.gab200_regularize_backward.restype = C.c_int32

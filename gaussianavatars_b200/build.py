@@ -27,6 +27,7 @@ SOURCES = {
     "tile_sort.cu": [],
     "densify.cu": [],
     "regularize.cu": [],
+    "nvls.cu": [],
     "blend.cu": [],
     "face_frame.cu": [],
     "loss.cu": [],

@@ -180,6 +180,9 @@ cudaError_t launch_densify_apply(const gab200_densify_args& a, const gab200_dens
 cudaError_t launch_regularize_forward(const gab200_regularize_args& a, cudaStream_t stream);
 cudaError_t launch_regularize_backward(const gab200_regularize_args& a, const float* g_out, cudaStream_t stream);
 
+// nvls.cu
+void launch_nvls_allreduce(float* mc, int64_t n, int rank, int world, cudaStream_t stream);
+
 // optim.cu
 void launch_adam(int num_segments, const gab200_adam_segment* segs, int64_t step, double beta1, double beta2, double eps,
                  cudaStream_t stream);

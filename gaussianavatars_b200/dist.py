@@ -85,11 +85,20 @@ class SymmetricGradBuffer:
     Falls back (attribute `.enabled` False) when the fabric has no multicast support; callers then use
     `allreduce_splat_grads` (one NCCL all-reduce)."""
 
-    def __init__(self, pc, group=None):
+    def __init__(self, pc, group=None, mode: str = "push"):
+        """mode "push": the backward kernel emits multimem.red into every replica (above).
+        mode "two_shot": the backward stores its gradients into the LOCAL replica with plain stores; `end()` then runs
+        the two-shot NVLS all-reduce of csrc/nvls.cu in place (multimem.ld_reduce of this rank's slice + multimem.st
+        to every replica) between two device-side group barriers.  (N-1)/N of the buffer crosses NVLink each way per
+        GPU instead of N x: this is the form that scales, and it is what bench.py uses for N > 1 when the fabric has
+        multicast."""
         import torch.distributed._symmetric_memory as symm_mem
 
+        if mode not in ("push", "two_shot"):
+            raise ValueError("mode must be 'push' or 'two_shot'")
         self.enabled = False
         self.pc = pc
+        self.mode = mode
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         group = group if group is not None else dist.group.WORLD
@@ -103,7 +112,8 @@ class SymmetricGradBuffer:
                 pass
             # two replicas used alternately: the one for step i+1 is zeroed during step i, so that only ONE group
             # barrier per step (end) sits on the critical path -- see begin()
-            self.flats = [symm_mem.empty(self.numel, dtype=torch.float32, device=device) for _ in range(2)]
+            self.flats = [symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+                          for _ in range(2 if mode == "push" else 1)]
             self.handles = [symm_mem.rendezvous(f, group) for f in self.flats]
             self.mc_ptrs = [int(h.multicast_ptr) for h in self.handles]
         except Exception as e:  # pragma: no cover - fabric / build dependent
@@ -126,7 +136,8 @@ class SymmetricGradBuffer:
         for f in self.flats:
             f.zero_()
         self.handles[0].barrier(channel=0)
-        self.cur = 1  # begin() flips first
+        self.cur = 1 if mode == "push" else 0  # push: begin() flips first
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
 
     @property
     def flat(self):
@@ -145,26 +156,62 @@ class SymmetricGradBuffer:
 
     def rebuild(self, group=None):
         """New symmetric buffers for the model's current parameters (collective: every rank must call it)."""
-        self.__init__(self.pc, group if group is not None else getattr(self, "group", None))
+        self.__init__(self.pc, group if group is not None else getattr(self, "group", None), mode=self.mode)
         if self.enabled:
             self.pc.symm_grad = self
         return self
 
+    def _two_shot(self):
+        import ctypes as C
+
+        from . import _native as N
+
+        h = self.handles[0]
+        h.barrier(channel=0)     # every rank's backward has written its replica
+        with torch.cuda.device(self.flats[0].device):
+            stream = torch.cuda.current_stream(self.flats[0].device).cuda_stream
+            N.check(N.lib().gab200_nvls_allreduce(C.c_void_p(self.mc_ptrs[0]), self.numel, self.rank, self.world,
+                                                  C.c_void_p(stream)), "gab200_nvls_allreduce")
+        h.barrier(channel=1)     # every slice has been stored into every replica
+
+    def self_test(self) -> bool:
+        """Collective (every rank calls it).  Reduces a known pattern through the two-shot kernel and checks the sums
+        on this rank; leaves the buffer zeroed.  bench.py falls back to NCCL when any rank reports False."""
+        if not self.enabled or self.mode != "two_shot":
+            return False
+        f = self.flats[0]
+        idx = torch.arange(self.numel, device=f.device, dtype=torch.float32)
+        f.copy_((idx % 13.0) * float(self.rank + 1))
+        self._two_shot()
+        want = (idx % 13.0) * float(self.world * (self.world + 1) // 2)
+        ok = bool(torch.equal(f, want))
+        self.handles[0].barrier(channel=0)   # nobody zeroes before everybody has compared
+        f.zero_()
+        self.handles[0].barrier(channel=1)
+        return ok
+
     def begin(self):
         """Call before backward.  Switches to the replica that every rank zeroed before the previous step's end()
         barrier, and zeroes the other one (whose sums the optimizer has consumed by now) for the step after."""
+        self.pc._gab200_mc_used = False  # the backward sets it when its gradients really went into this buffer
+        if self.mode == "two_shot":
+            return                       # the backward overwrites every element of the local replica: nothing to zero
         prev = self.cur
         self.cur ^= 1
         self.flats[prev].zero_()
-        self.pc._gab200_mc_used = False  # the backward sets it when its gradients really went through the multicast
 
     def end(self):
         """Call after backward.  Group barrier; then the parameters' .grad are pointed at the reduced replica -- but
         only if this step's backward took the multicast path for exactly these parameters.  Otherwise (override_color,
         a model whose parameters were replaced or resized since the buffer was built) the locally stored gradients are
         the valid ones: they are summed with one NCCL all-reduce instead, and the zeroed replica is left alone."""
-        self.handles[self.cur].barrier(channel=1)
-        if getattr(self.pc, "_gab200_mc_used", False) and self.matches():
+        took = getattr(self.pc, "_gab200_mc_used", False) and self.matches()
+        if self.mode == "two_shot":
+            if took:
+                self._two_shot()
+        else:
+            self.handles[self.cur].barrier(channel=1)
+        if took:
             # autograd may have CLONED the gradient views while the reduction was still in flight (it only adopts a
             # tensor it holds the sole reference to): point .grad at the reduced buffer itself.  With
             # zero_grad(set_to_none=False) autograd would accumulate INTO a replica that must read zero at its next

@@ -55,7 +55,8 @@ def camera_block(cam) -> torch.Tensor:
 class GraphedFrame:
     def __init__(self, pc, width: int, height: int, fovx: float, fovy: float, bg: torch.Tensor, loss: str = "l1_u8",
                  lambda_dssim: float = 0.2, host_inputs: bool = False, capacity: Optional[int] = None,
-                 headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None):
+                 headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None,
+                 before_backward=None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
         host_inputs: the frame owns pinned STAGING tensors (`cam_stage` (35,) float32, `gt_stage` (3,H,W) uint8) that a
@@ -77,6 +78,7 @@ class GraphedFrame:
         self.pc, self.W, self.H, self.fovx, self.fovy = pc, int(width), int(height), float(fovx), float(fovy)
         self.loss_kind, self.lambda_dssim, self.host_inputs = loss, float(lambda_dssim), bool(host_inputs)
         self.after_backward = after_backward
+        self.before_backward = before_backward   # e.g. SymmetricGradBuffer.begin
         self.regularizers = regularizers
         if regularizers is not None and loss == "dL_dimage":
             raise ValueError("regularizers need a scalar loss ('l1_u8' or 'photometric')")
@@ -179,9 +181,13 @@ class GraphedFrame:
                 lx, ls = binding_regularizers(pc._xyz, pc._scaling, out["radii"], getattr(pc, "binding", None),
                                               getattr(pc, "face_scaling", None), **self.regularizers)
                 loss = loss + lx + ls
+            if self.before_backward is not None:
+                self.before_backward()
             loss.backward()
         else:
             loss = None
+            if self.before_backward is not None:
+                self.before_backward()
             img.backward(self.dL_dimage)
         if self.after_backward is not None:
             self.after_backward()

@@ -462,8 +462,11 @@ class _RasterizeBound(torch.autograd.Function):
         widths = (3, 4, 3, 1, 3, 3 * (M - 1))
         # frame-sharded data parallel with NVLS: the gradients are reduced INTO the symmetric buffer by the kernel
         symm = getattr(ctx.grad_sink, "symm_grad", None) if ctx.grad_sink is not None else None
-        use_mc = symm is not None and symm.enabled and symm.numel == P * sum(widths) and colors_precomp is None
-        flat = symm.flat if use_mc else torch.empty((P * sum(widths),), dtype=torch.float32, device=device)
+        use_symm = symm is not None and symm.enabled and symm.numel == P * sum(widths) and colors_precomp is None
+        # "push": the kernel reduces into every replica with multimem.red; "two_shot": plain stores into the local
+        # replica, reduced afterwards by the NVLS all-reduce kernel (dist.SymmetricGradBuffer.end)
+        use_mc = use_symm and getattr(symm, "mode", "push") == "push"
+        flat = symm.flat if use_symm else torch.empty((P * sum(widths),), dtype=torch.float32, device=device)
         views, off = [], 0
         for w in widths:
             views.append(flat[off:off + P * w])
@@ -504,7 +507,7 @@ class _RasterizeBound(torch.autograd.Function):
         ctx.holder = None
         if ctx.grad_sink is not None:  # dist.py: ONE all-reduce over this buffer instead of six
             ctx.grad_sink.flat_grad = flat
-            ctx.grad_sink._gab200_mc_used = bool(use_mc)  # SymmetricGradBuffer.end() only trusts the replica if set
+            ctx.grad_sink._gab200_mc_used = bool(use_symm)  # SymmetricGradBuffer.end() only trusts the replica if set
         return (d_xyz, d_means2D, d_rot, d_scale, d_opac, d_dc, d_rest, d_fc, d_fR, d_fs, None, d_colors, None, None)
 
 

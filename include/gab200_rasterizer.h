@@ -336,6 +336,13 @@ typedef struct gab200_regularize_args {
 int32_t gab200_regularize_forward(const gab200_regularize_args* args, void* stream);
 int32_t gab200_regularize_backward(const gab200_regularize_args* args, const float* g_out, void* stream);
 
+/* In-place all-reduce (sum) of n floats that every rank of a group holds in NVLink symmetric memory, through the
+ * NVSwitch multicast address `mc_ptr` of that allocation (NVLS): rank r reduces the r-th slice with
+ * multimem.ld_reduce and stores it to every replica with multimem.st.  16-byte aligned.  The CALLER orders it between
+ * two group barriers on the stream (every replica written before / every slice stored after): dist.py uses the
+ * symmetric-memory signal pads.  Replaces the ncclAllReduce of the flat splat-gradient buffer. */
+int32_t gab200_nvls_allreduce(float* mc_ptr, int64_t n, int32_t rank, int32_t world, void* stream);
+
 /* densify_and_prune of the splat arrays with the Adam-state surgery fused.  Replaces
  * GaussianModel.densify_and_prune (scene/gaussian_model.py:503-519 -> densify_and_clone :481-501, densify_and_split
  * :451-479, prune_points :371-397) together with the optimizer surgery it drives (:334-369, :399-424) and the

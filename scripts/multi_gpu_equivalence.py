@@ -5,7 +5,7 @@ cameras and all-reduce the flat gradient buffer == one rank accumulating the gra
 
 Checks, for C cameras sharded round-robin: (a) eager render() + dist.allreduce_splat_grads, (b) the same step replayed
 as a CUDA graph with the NCCL all-reduce captured inside, (c) the NVLS multimem.red path (SymmetricGradBuffer) when the
-fabric offers multicast.  Rank 0 prints one JSON line and exits non-zero on a mismatch."""
+fabric offers multicast, (d) the two-shot NVLS all-reduce kernel (csrc/nvls.cu), eager and captured inside the graph.  Rank 0 prints one JSON line and exits non-zero on a mismatch."""
 import json
 import math
 import os
@@ -105,7 +105,40 @@ def main():
     else:
         out["nvls_multimem"] = None
         out["nvls_unavailable"] = getattr(symm, "error", "?")
-    t = torch.tensor([max(v for k, v in out.items() if k in ("eager_nccl", "graph_nccl", "nvls_multimem") and v is not None)],
+    # (d) two-shot NVLS all-reduce kernel on the symmetric buffer: eager, then captured inside the step's graph
+    pc = model()
+    symm = gdist.SymmetricGradBuffer(pc, mode="two_shot")
+    if symm.enabled:
+        pc.symm_grad = symm
+        out["nvls2_self_test"] = symm.self_test()
+        acc = torch.zeros_like(ref)
+        for i in mine:
+            for p in pc.parameters():
+                p.grad = None
+            pc.update_mesh_properties(syn.pose_mesh(pc.verts_rest, cams[i].timestep).contiguous())
+            o = render(cams[i].to(dev), pc, Pipe, bg)
+            symm.begin()
+            o["render"].backward(gout)
+            assert symm.end(), "the symmetric buffer was not used"
+            acc += torch.cat([p.grad.reshape(-1) for p in pc.parameters()])
+        out["nvls2_eager"] = float((acc - ref).abs().max()) / scale
+        fr2 = GraphedFrame(pc, W, H, cams[0].FoVx, cams[0].FoVy, bg, loss="dL_dimage",
+                           warm_cameras=[camera_block(cams[i]).to(dev) for i in mine],
+                           before_backward=symm.begin, after_backward=symm.end)
+        fr2.set_inputs(camera=camera_block(cams[mine[0]]).to(dev), verts=pc.verts_rest, dL_dimage=gout)
+        fr2.capture()
+        acc = torch.zeros_like(ref)
+        for i in mine:
+            fr2.set_inputs(camera=camera_block(cams[i]).to(dev), verts=syn.pose_mesh(pc.verts_rest, cams[i].timestep))
+            fr2.run(check=True)
+            acc += torch.cat([p.grad.reshape(-1) for p in pc.parameters()])
+        out["nvls2_graph"] = float((acc - ref).abs().max()) / scale
+        if not out["nvls2_self_test"]:
+            out["nvls2_graph"] = 1.0
+    else:
+        out["nvls2_eager"] = out["nvls2_graph"] = None
+    t = torch.tensor([max(v for k, v in out.items()
+                          if k in ("eager_nccl", "graph_nccl", "nvls_multimem", "nvls2_eager", "nvls2_graph") and v is not None)],
                      device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = float(t) < 2e-5
