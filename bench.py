@@ -77,6 +77,11 @@ def parse():
                          "preprocess_bwd (eager only; loses at N=8, every replica receives N x the buffer).  auto = "
                          "nvls2 when the fabric has multicast and its self-test passes on every rank, else nccl "
                          "(DESIGN.md section 6)")
+    ap.add_argument("--reduce", default="deferred", choices=["deferred", "sync"],
+                    help="N>1: deferred = the all-reduce of step i's gradient buffer runs as a forked branch of step i+1's "
+                         "graph (two graphs / two buffers used alternately; the K-th reduction is drained inside the timed "
+                         "region); sync = the collective sits after backward inside the same graph.  The sync figure is "
+                         "measured and reported either way (`sync_collective`)")
     ap.add_argument("--splats", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -304,25 +309,44 @@ def main():
     verts, faces = syn.head_mesh()
     params = syn.avatar_splats(P_SPLATS, n_faces=faces.shape[0], seed=0, sh_degree=SH_DEGREE)
     pc = MeshBoundGaussians(params, SH_DEGREE, verts, faces, pose_fn=syn.pose_mesh, device=dev, requires_grad=True)
-    symm, collective_note = None, None
-    if world > 1 and args.collective != "nccl":
-        mode = "push" if args.collective == "nvls" else "two_shot"
-        why = None
-        try:
-            symm = gdist.SymmetricGradBuffer(pc, mode=mode)
-            ok = symm.enabled and (mode == "push" or symm.self_test())
-            if not ok:
-                why = getattr(symm, "error", "self-test of the two-shot kernel failed")
-        except Exception as e:
-            ok, why = False, f"{type(e).__name__}: {e}"
-        flag = torch.tensor([1.0 if ok else 0.0], device=dev)
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if float(flag) == 0.0:
-            if args.collective != "auto":
-                raise RuntimeError(f"--collective {args.collective} unavailable: {why or 'another rank failed'}")
-            symm, collective_note = None, f"nvls2 unavailable ({why or 'another rank failed'}): nccl"
+    # N > 1: caller-owned gradient buffers (dist.SymmetricGradBuffer).  bufs[0] doubles as the buffer of the synchronous
+    # step; the pair serves the two alternating graphs of the deferred reduction.
+    symm, bufs, collective_note = None, None, None
+    if world > 1:
+        def agree(ok):
+            flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            return float(flag) != 0.0
+
+        def make(mode, n):
+            why, made = None, []
+            try:
+                made = [gdist.SymmetricGradBuffer(pc, mode=mode) for _ in range(n)]
+                ok = all(b.enabled for b in made) and (mode != "two_shot" or all(b.self_test() for b in made))
+                if not ok:
+                    why = next((getattr(b, "error", None) for b in made if getattr(b, "error", None)), "self-test failed")
+            except Exception as e:
+                ok, why = False, f"{type(e).__name__}: {e}"
+            return (made if agree(ok) else None), why
+
+        if args.collective == "nvls":      # push-style multimem.red from the backward kernel: eager only
+            made, why = make("push", 1)
+            if made is None:
+                raise RuntimeError(f"--collective nvls unavailable: {why or 'another rank failed'}")
+            symm = made[0]
         else:
-            pc.symm_grad = symm
+            if args.collective in ("auto", "nvls2"):
+                bufs, why = make("two_shot", 2)
+                if bufs is None:
+                    if args.collective == "nvls2":
+                        raise RuntimeError(f"--collective nvls2 unavailable: {why or 'another rank failed'}")
+                    collective_note = f"nvls2 unavailable ({why or 'another rank failed'}): nccl"
+            if bufs is None:
+                bufs, why = make("plain", 2)
+                if bufs is None:
+                    raise RuntimeError(f"gradient buffers could not be created: {why}")
+            symm = bufs[0]
+        pc.symm_grad = symm
     cams_host = make_cameras(N_CAMERAS)
     my_cams = [cams_host[i] for i in gdist.shard_frames(N_CAMERAS, rank, world)] or cams_host
     cams_dev = [c.to(dev) for c in my_cams]
@@ -371,7 +395,7 @@ def main():
     # ---- timed region: HBM-resident, L2 flushed between steps, per-step CUDA events -------------------------
     K = args.steps
 
-    def timed_pass(step, stage_events: bool):
+    def timed_pass(step, stage_events: bool, tail=None):
         N.stage_timing(stage_events)
         N.stage_times(reset=True)
         N.host_times(reset=True)
@@ -386,6 +410,12 @@ def main():
                 starts[i].record()
                 step(i)
                 ends[i].record()
+            if tail is not None:   # work the K steps left pending (the K-th deferred reduction): timed, added
+                starts.append(torch.cuda.Event(enable_timing=True))
+                ends.append(torch.cuda.Event(enable_timing=True))
+                starts[-1].record()
+                tail()
+                ends[-1].record()
             barrier()
             w1 = time.perf_counter()
         st_ = N.stage_times(reset=True)
@@ -407,60 +437,92 @@ def main():
 
     cam_blocks_dev = [camera_block(c) for c in cams_dev]
     c0 = my_cams[0]
-    use_graph = not args.no_graph and (symm is None or symm.mode == "two_shot")
-    frame = None
+    from gaussianavatars_b200.graph import pair_with_deferred_reduce
+
+    use_graph = not args.no_graph and (symm is None or symm.mode != "push")
+    frames = []          # the resident step: one graph, or the alternating pair of the deferred reduction
     graph_note = None
+    n_common = max(1, N_CAMERAS // world)   # warm-up frames issue collectives: every rank must run the same number
 
-    def hooks():
-        """(before_backward, after_backward) of the captured step for the collective in use."""
-        if world == 1:
-            return None, None
-        if symm is not None:
-            return symm.begin, symm.end
-        return None, (lambda: gdist.allreduce_splat_grads(pc))
+    def sync_hooks():
+        """(before_backward, after_backward) of a step whose collective sits after backward in the same graph."""
+        return (None, None) if world == 1 else (symm.begin, symm.end)
 
-    def try_capture():
-        """The resident step as a graph; None (+ reason) if it cannot be captured.  Every rank must agree."""
-        fr, why = None, None
+    def attach_sync():
+        if world > 1:
+            pc.symm_grad = symm
+
+    def capture_agreed(build):
+        """build() -> captured frame(s); None (+ reason) if any rank could not (a captured collective cannot meet an
+        eager one, so every rank must take the same path)."""
+        got, why = None, None
         try:
-            before, after = hooks()
-            fr = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev,
-                              before_backward=before, after_backward=after)
-            fr.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
-            fr.capture()
+            got = build()
         except Exception as e:  # e.g. a fabric on which the collective cannot be captured
-            fr, why = None, f"{type(e).__name__}: {e}"
-        if world > 1:  # a captured collective cannot meet an eager one
-            flag = torch.tensor([1.0 if fr is not None else 0.0], device=dev)
-            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            if float(flag) == 0.0:
-                fr, why = None, why or "another rank could not capture the step"
-        return fr, why
+            got, why = None, f"{type(e).__name__}: {e}"
+        if world > 1 and not agree(got is not None):
+            got, why = None, why or "another rank could not capture the step"
+        return got, why
 
-    if use_graph:
-        frame, why = try_capture()
-        if frame is None and symm is not None and args.collective == "auto":
-            # the two-shot kernel + signal-pad barriers could not be captured here: NCCL inside the graph instead
-            collective_note = f"nvls2 not capturable ({why}): nccl"
-            symm = None
-            del pc.symm_grad
-            frame, why = try_capture()
-        if frame is None:
-            use_graph, graph_note = False, f"graph capture failed ({why}); eager step timed"
+    def build_sync():
+        attach_sync()
+        before, after = sync_hooks()
+        fr = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage", warm_cameras=cam_blocks_dev[:n_common],
+                          before_backward=before, after_backward=after)
+        fr.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
+        fr.capture()
+        return [fr]
+
+    def build_deferred():
+        pair = []
+        for k in range(2):
+            fr = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="dL_dimage",
+                              warm_cameras=cam_blocks_dev[:n_common])
+            fr.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
+            pair.append(fr)
+        pair_with_deferred_reduce(pair, bufs)
+        for fr in pair:
+            fr.capture()
+        return pair
 
     def step_resident(i):
-        if frame is None:
+        if not frames:
             return step_eager(i)
-        frame.set_inputs(camera=cam_blocks_dev[i % len(cam_blocks_dev)], verts=posed[i % len(posed)].detach())
-        frame.run()
+        fr = frames[i % len(frames)]
+        fr.set_inputs(camera=cam_blocks_dev[i % len(cam_blocks_dev)], verts=posed[i % len(posed)].detach())
+        fr.run()
+
+    def drain():
+        """Deferred reduction: the gradients of the last of K steps are still unreduced -- reduce them now."""
+        bufs[(K - 1) % 2].reduce()
+
+    sync_line, deferred = None, False
+    if use_graph:
+        frames, why = capture_agreed(build_sync)
+        if frames is None:
+            frames, use_graph, graph_note = [], False, f"graph capture failed ({why}); eager step timed"
+    if use_graph and world > 1 and args.reduce == "deferred" and bufs is not None:
+        # the synchronous form first (reported beside the headline), then the deferred pair
+        for i in range(max(args.warmup, 3)):
+            step_resident(i)
+        barrier()
+        ms_sync, _, _, _, _, _ = timed_pass(step_resident, False)
+        sync_line = {"value": world * K / (ms_sync / 1e3), "unit": "frames/s", "ms_per_step": ms_sync / K,
+                     "what": "collective after backward inside the same graph (on the critical path)"}
+        pair, why = capture_agreed(build_deferred)
+        if pair is None:
+            graph_note = f"deferred-reduction pair not capturable ({why}); synchronous step timed"
+            attach_sync()
+        else:
+            frames, deferred = pair, True
 
     for i in range(max(args.warmup, 3)):
         step_resident(i)
     barrier()
 
-    # the headline number: nothing but the K steps inside the event pairs
-    ms_total, _, clk, wall_timed, _, _ = timed_pass(step_resident, False)
-    overflow_steps = bool(frame is not None and frame.overflowed(wait=True))
+    # the headline number: nothing but the K steps (+ the drained K-th reduction) inside the event pairs
+    ms_total, _, clk, wall_timed, _, _ = timed_pass(step_resident, False, tail=drain if deferred else None)
+    overflow_steps = any(fr.overflowed(wait=True) for fr in frames)
 
     # ---- warm-L2 variant (no flush), whole-loop events: what a training loop actually sees -------------------
     barrier()
@@ -468,6 +530,8 @@ def main():
     e0.record()
     for i in range(K):
         step_resident(i)
+    if deferred:
+        drain()
     e1.record()
     barrier()
     ms_warm = e0.elapsed_time(e1)
@@ -482,10 +546,12 @@ def main():
         # two graphs, each reading its own pinned ground-truth staging buffer (a loader fills one while the GPU reads
         # the other); camera block staged in pinned memory per step; loss scalar copied back by the graph, read late
         e2e_frames = []
+        if not deferred:
+            attach_sync()
         for k in range(2):
-            before_, after_ = hooks()
+            before_, after_ = (None, None) if deferred else sync_hooks()
             f_ = GraphedFrame(pc, WIDTH, HEIGHT, c0.FoVx, c0.FoVy, bg, loss="l1_u8", host_inputs=True,
-                              warm_cameras=cam_host_blocks, before_backward=before_, after_backward=after_)
+                              warm_cameras=cam_host_blocks[:n_common], before_backward=before_, after_backward=after_)
             f_.gt_stage.copy_(gt_host[k])   # the loader's job: decoded frames land in the two pinned staging buffers
             f_.cam_stage.copy_(cam_host_blocks[0])
             f_.set_inputs(verts=posed[0].detach())
@@ -493,6 +559,8 @@ def main():
             e2e_frames.append(f_)
         e2e_frames[0].prefetch_for(e2e_frames[1])
         e2e_frames[1].prefetch_for(e2e_frames[0])
+        if deferred:   # each graph's forked branch also all-reduces the other frame's gradient buffer
+            pair_with_deferred_reduce(e2e_frames, bufs)
         for f_ in e2e_frames:
             f_.capture()
         done = [torch.cuda.Event() for _ in range(2)]
@@ -511,6 +579,8 @@ def main():
                 losses.append(float(e2e_frames[(i - 1) % 2].loss_host))
 
         def finish_e2e(last):
+            if deferred:
+                drain()
             done[last % 2].synchronize()
             losses.append(float(e2e_frames[last % 2].loss_host))
     else:
@@ -645,13 +715,18 @@ def main():
         "config": {"workload": WORKLOAD, "splats": P_SPLATS, "width": WIDTH, "height": HEIGHT, "sh_degree": SH_DEGREE,
                    "faces": F, "instances_per_frame": int(n_inst), "binning": "exact" if args.exact_binning else "culled",
                    "frames_per_step_per_gpu": 1, "parallelism": f"frame-sharded dp{world}",
-                   "step": ("one CUDA-graph replay (face frame + fused fwd + bwd" + (" + gradient all-reduce" if world > 1 else "") + ")")
+                   "step": (("one CUDA-graph replay (face frame + fused fwd + bwd" +
+                             ("" if world == 1 else
+                              "; forked branch: all-reduce of the PREVIOUS step's gradient buffer -- two graphs and two "
+                              "buffers used alternately, the K-th reduction drained inside the timed region" if deferred
+                              else " + gradient all-reduce") + ")") + (f" [{graph_note}]" if graph_note else ""))
                            if use_graph else (graph_note or "eager render() + autograd"),
                    "grad_collective": ("none" if world == 1 else
-                                       "nccl all-reduce of the flat buffer" if symm is None else
+                                       "nccl all-reduce of the caller-owned flat buffer" if symm.mode == "plain" else
                                        "nvls multimem.red fused in preprocess_bwd" if symm.mode == "push" else
                                        "nvls two-shot all-reduce kernel (multimem.ld_reduce + multimem.st) on the "
                                        "symmetric flat buffer, between two signal-pad barriers, inside the graph"),
+                   "reduction": "none" if world == 1 else ("deferred by one replay" if deferred else "synchronous"),
                    **({"collective_note": collective_note} if collective_note else {}),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
         "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},
@@ -661,6 +736,7 @@ def main():
                 "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": 4,
                 "path": ("two GraphedFrame(host_inputs=True, loss='l1_u8') prefetching each other's inputs from pinned "
                          "staging inside their graphs") if use_graph else "eager render() + l1_loss_u8"},
+        **({"sync_collective": sync_line} if sync_line else {}),
         "gpu_launches": int(launches),
         "graph_overflow": bool(overflow_steps),
         "clocks": clk.summary(),

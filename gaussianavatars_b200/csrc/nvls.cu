@@ -68,7 +68,11 @@ void launch_nvls_allreduce(float* mc, int64_t n, int rank, int world, cudaStream
   const int64_t tail0 = last ? quads * 4 : 0, tail1 = last ? n : 0;
   int64_t blocks = (q1 - q0 + 255) / 256;
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;   // a few CTAs per SM keep enough multimem requests in flight
+  const int knob = tune_get(GAB200_TUNE_NVLS_CTAS);
+  // measured on 2 B200s (profiles/r02/nvls_probe_n2.json): 32 .. 1184 CTAs all take 70-80 us for 23.6 MB -- the switch,
+  // not the issue rate, is the limit -- so the kernel stays small and leaves the SMs to the frame it runs beside
+  const int64_t cap = knob > 0 ? knob : 64;
+  if (blocks > cap) blocks = cap;
   nvls_allreduce_kernel<<<(unsigned)blocks, 256, 0, stream>>>(mc, q0, q1, tail0, tail1);
   count_launch();
 }

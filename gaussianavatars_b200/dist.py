@@ -91,36 +91,32 @@ class SymmetricGradBuffer:
         the two-shot NVLS all-reduce of csrc/nvls.cu in place (multimem.ld_reduce of this rank's slice + multimem.st
         to every replica) between two device-side group barriers.  (N-1)/N of the buffer crosses NVLink each way per
         GPU instead of N x: this is the form that scales, and it is what bench.py uses for N > 1 when the fabric has
-        multicast."""
+        multicast.
+        mode "plain": an ordinary device buffer, reduced by ncclAllReduce -- the same caller-owned-buffer protocol
+        (begin / end / reduce) on a fabric without multicast.
+
+        In the "two_shot" and "plain" modes the buffer is PERSISTENT and caller-owned, which is what lets the reduction
+        be deferred: `end(reduce=False)` adopts the local gradients, and `reduce()` can be issued later -- on another
+        stream, or as a forked branch of the NEXT step's CUDA graph (graph.GraphedFrame side_work), where it runs under
+        that step's forward + backward."""
         import torch.distributed._symmetric_memory as symm_mem
 
-        if mode not in ("push", "two_shot"):
-            raise ValueError("mode must be 'push' or 'two_shot'")
+        if mode not in ("push", "two_shot", "plain"):
+            raise ValueError("mode must be 'push', 'two_shot' or 'plain'")
         self.enabled = False
         self.pc = pc
         self.mode = mode
+        self.collective = "nvls" if mode == "two_shot" else "nccl"   # what reduce() issues (two_shot may use either)
         if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
             return
         group = group if group is not None else dist.group.WORLD
         params = list(pc.parameters())
         self.numel = sum(p.numel() for p in params)
         device = params[0].device
-        try:
-            try:
-                symm_mem.set_backend("CUDA")
-            except Exception:
-                pass
-            # two replicas used alternately: the one for step i+1 is zeroed during step i, so that only ONE group
-            # barrier per step (end) sits on the critical path -- see begin()
-            self.flats = [symm_mem.empty(self.numel, dtype=torch.float32, device=device)
-                          for _ in range(2 if mode == "push" else 1)]
-            self.handles = [symm_mem.rendezvous(f, group) for f in self.flats]
-            self.mc_ptrs = [int(h.multicast_ptr) for h in self.handles]
-        except Exception as e:  # pragma: no cover - fabric / build dependent
-            self.error = repr(e)
-            return
-        if 0 in self.mc_ptrs:
-            self.error = "no NVLS multicast support on this fabric"
+        if mode == "plain":
+            self.flats = [torch.zeros(self.numel, dtype=torch.float32, device=device)]
+            self.handles, self.mc_ptrs = [None], [0]
+        elif not self._alloc_symmetric(symm_mem, device, group):
             return
         self.enabled = True
         self.group = group
@@ -135,9 +131,30 @@ class SymmetricGradBuffer:
             self.all_views.append(views)
         for f in self.flats:
             f.zero_()
-        self.handles[0].barrier(channel=0)
+        if self.handles[0] is not None:
+            self.handles[0].barrier(channel=0)
         self.cur = 1 if mode == "push" else 0  # push: begin() flips first
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def _alloc_symmetric(self, symm_mem, device, group) -> bool:
+        try:
+            try:
+                symm_mem.set_backend("CUDA")
+            except Exception:
+                pass
+            # push: two replicas used alternately: the one for step i+1 is zeroed during step i, so that only ONE group
+            # barrier per step (end) sits on the critical path -- see begin()
+            self.flats = [symm_mem.empty(self.numel, dtype=torch.float32, device=device)
+                          for _ in range(2 if self.mode == "push" else 1)]
+            self.handles = [symm_mem.rendezvous(f, group) for f in self.flats]
+            self.mc_ptrs = [int(h.multicast_ptr) for h in self.handles]
+        except Exception as e:  # pragma: no cover - fabric / build dependent
+            self.error = repr(e)
+            return False
+        if 0 in self.mc_ptrs:
+            self.error = "no NVLS multicast support on this fabric"
+            return False
+        return True
 
     @property
     def flat(self):
@@ -174,6 +191,16 @@ class SymmetricGradBuffer:
                                                   C.c_void_p(stream)), "gab200_nvls_allreduce")
         h.barrier(channel=1)     # every slice has been stored into every replica
 
+    def reduce(self):
+        """Sum the buffer over the ranks, in place, on the current stream ("two_shot" / "plain" modes).  Stream-ordered,
+        no host wait; capturable.  The caller orders it after the backward that filled the buffer."""
+        if self.mode == "push":
+            raise RuntimeError("push mode reduces inside the backward kernel")
+        if self.mode == "two_shot" and self.collective == "nvls":
+            self._two_shot()
+        else:
+            dist.all_reduce(self.flats[0], op=dist.ReduceOp.SUM, group=self.group)
+
     def self_test(self) -> bool:
         """Collective (every rank calls it).  Reduces a known pattern through the two-shot kernel and checks the sums
         on this rank; leaves the buffer zeroed.  bench.py falls back to NCCL when any rank reports False."""
@@ -194,21 +221,22 @@ class SymmetricGradBuffer:
         """Call before backward.  Switches to the replica that every rank zeroed before the previous step's end()
         barrier, and zeroes the other one (whose sums the optimizer has consumed by now) for the step after."""
         self.pc._gab200_mc_used = False  # the backward sets it when its gradients really went into this buffer
-        if self.mode == "two_shot":
-            return                       # the backward overwrites every element of the local replica: nothing to zero
+        if self.mode != "push":
+            return                       # the backward overwrites every element of the local buffer: nothing to zero
         prev = self.cur
         self.cur ^= 1
         self.flats[prev].zero_()
 
-    def end(self):
-        """Call after backward.  Group barrier; then the parameters' .grad are pointed at the reduced replica -- but
+    def end(self, reduce: bool = True):
+        """Call after backward.  reduce=False ("two_shot" / "plain"): adopt the LOCAL gradients only -- the caller
+        issues `reduce()` later (deferred reduction).  Group barrier; then the parameters' .grad are pointed at the reduced replica -- but
         only if this step's backward took the multicast path for exactly these parameters.  Otherwise (override_color,
         a model whose parameters were replaced or resized since the buffer was built) the locally stored gradients are
         the valid ones: they are summed with one NCCL all-reduce instead, and the zeroed replica is left alone."""
         took = getattr(self.pc, "_gab200_mc_used", False) and self.matches()
-        if self.mode == "two_shot":
-            if took:
-                self._two_shot()
+        if self.mode != "push":
+            if took and reduce:
+                self.reduce()
         else:
             self.handles[self.cur].barrier(channel=1)
         if took:
@@ -219,5 +247,6 @@ class SymmetricGradBuffer:
             for p, v in zip(self.params, self.all_views[self.cur]):
                 p.grad = v
             return True
-        allreduce_splat_grads(self.pc, group=self.group)
+        if reduce:
+            allreduce_splat_grads(self.pc, group=self.group)
         return False

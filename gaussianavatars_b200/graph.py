@@ -52,11 +52,42 @@ def camera_block(cam) -> torch.Tensor:
                       cam.camera_center.reshape(-1).float()))
 
 
+def pair_with_deferred_reduce(frames, buffers):
+    """Two frames of one model used alternately, each with its own caller-owned gradient buffer
+    (dist.SymmetricGradBuffer, mode "two_shot" or "plain"): frame k's backward fills buffers[k], and a forked branch of
+    frame k's graph all-reduces buffers[1-k] -- the gradients of the PREVIOUS step -- while frame k computes.  After
+    replay i the reduced gradients of step i-1 are in buffers[1-k] (`reduced_grads(frames, buffers, k)`), those of
+    step i become available after replay i+1 or `buffers[k].reduce()`.  The collective leaves the critical path; the
+    price is that an optimizer consuming reduced gradients runs one replay behind.
+    Call before capture()."""
+    if len(frames) != 2 or len(buffers) != 2:
+        raise ValueError("a deferred-reduction pair is two frames and two buffers")
+    for k, f in enumerate(frames):
+        mine, other = buffers[k], buffers[1 - k]
+
+        def before(f=f, mine=mine):
+            f.pc.symm_grad = mine
+            mine.begin()
+
+        f.before_backward = before
+        f.after_backward = lambda mine=mine: mine.end(reduce=False)
+        f.side_work = other.reduce
+        if f._side is None:
+            f._side = torch.cuda.Stream(device=f.device)
+    return frames
+
+
+def reduced_grads(buffers, k):
+    """Views (in pc.parameters() order) of the all-reduced gradients available after replaying frame k of a
+    deferred-reduction pair: those of the step before."""
+    return buffers[1 - k].all_views[0]
+
+
 class GraphedFrame:
     def __init__(self, pc, width: int, height: int, fovx: float, fovy: float, bg: torch.Tensor, loss: str = "l1_u8",
                  lambda_dssim: float = 0.2, host_inputs: bool = False, capacity: Optional[int] = None,
                  headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None,
-                 before_backward=None):
+                 before_backward=None, side_work=None):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
         host_inputs: the frame owns pinned STAGING tensors (`cam_stage` (35,) float32, `gt_stage` (3,H,W) uint8) that a
@@ -70,6 +101,10 @@ class GraphedFrame:
         by the full 124 us of that transfer; and ordering uploads against replays with cross-stream events costs
         ~40 us per step, profiles/r02/e2e_loop_probe.json.)
         after_backward: optional callable run inside the capture after backward (e.g. the gradient all-reduce).
+        before_backward: the same, right before backward (e.g. attach this frame's gradient buffer to the model).
+        side_work: optional callable captured on a FORKED branch of the graph that runs concurrently with the whole
+        frame and is joined at its end -- e.g. the all-reduce of the PREVIOUS step's gradient buffer
+        (dist.SymmetricGradBuffer.reduce of the other frame of an alternating pair), which then costs no step time.
         warm_cameras: camera blocks (35,) rendered eagerly before the capture to size the instance capacity.
         regularizers: keyword arguments of `binding_regularizers` (threshold_xyz, lambda_scale, ...; {} = the
         reference's defaults): the position / scale terms of train.py:134-146 are added to the loss inside the graph."""
@@ -79,6 +114,7 @@ class GraphedFrame:
         self.loss_kind, self.lambda_dssim, self.host_inputs = loss, float(lambda_dssim), bool(host_inputs)
         self.after_backward = after_backward
         self.before_backward = before_backward   # e.g. SymmetricGradBuffer.begin
+        self.side_work = side_work
         self.regularizers = regularizers
         if regularizers is not None and loss == "dL_dimage":
             raise ValueError("regularizers need a scalar loss ('l1_u8' or 'photometric')")
@@ -104,7 +140,8 @@ class GraphedFrame:
         self.slot = None
         self.replays = 0
         self.captures = 0
-        self._side = torch.cuda.Stream(device=dev) if host_inputs else None
+        self._side = torch.cuda.Stream(device=dev) if (host_inputs or side_work is not None) else None
+        self._uploads = bool(host_inputs)
         self._capacity = capacity
         self._warm = list(warm_cameras) if warm_cameras is not None else None
 
@@ -113,7 +150,7 @@ class GraphedFrame:
         """Copies new inputs into the static buffers (device tensors) / staging buffers (host_inputs)."""
         if camera is not None:
             blk = camera if isinstance(camera, torch.Tensor) else camera_block(camera)
-            if blk.device.type == "cpu" and self._side is not None:
+            if blk.device.type == "cpu" and self._uploads:
                 if not blk.is_pinned():      # stage pageable memory (after any upload still reading the staging copy)
                     self._side.synchronize()
                     self.cam_host.copy_(blk)
@@ -125,7 +162,7 @@ class GraphedFrame:
             with torch.no_grad():
                 self.verts.copy_(verts.reshape(self.verts.shape), non_blocking=True)
         if gt_u8 is not None:
-            if gt_u8.device.type == "cpu" and self._side is not None:
+            if gt_u8.device.type == "cpu" and self._uploads:
                 self._upload(self.gt, gt_u8)
             else:
                 self.gt.copy_(gt_u8, non_blocking=True)
@@ -165,13 +202,17 @@ class GraphedFrame:
             p.grad = None
         self.verts.grad = None
         other = self._prefetch_target
-        if other is not None:   # forked branch: the other frame's next inputs travel while this frame computes
+        forked = other is not None or self.side_work is not None
+        if forked:   # forked branch: runs while this frame computes
             cur = torch.cuda.current_stream(self.device)
             self._side.wait_stream(cur)
             with torch.cuda.stream(self._side):
-                other.cam.copy_(other.cam_stage, non_blocking=True)
-                if other.gt_stage is not None:
-                    other.gt.copy_(other.gt_stage, non_blocking=True)
+                if other is not None:   # the other frame's next inputs travel
+                    other.cam.copy_(other.cam_stage, non_blocking=True)
+                    if other.gt_stage is not None:
+                        other.gt.copy_(other.gt_stage, non_blocking=True)
+                if self.side_work is not None:
+                    self.side_work()
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
         img = out["render"]
@@ -194,7 +235,7 @@ class GraphedFrame:
         if loss is not None:
             self.loss = loss.detach()
             self.loss_host.copy_(self.loss, non_blocking=True)
-        if other is not None:   # join the branch (a captured fork must end inside the graph)
+        if forked:   # join the branch (a captured fork must end inside the graph)
             torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.image, self.radii, self.viewspace_points = img.detach(), out["radii"], out["viewspace_points"]
 
@@ -257,7 +298,7 @@ class GraphedFrame:
             self._gt_ready = None
         self.graph.replay()
         self.replays += 1
-        if self._side is not None:
+        if self._uploads:
             self._done = torch.cuda.Event()
             self._done.record()
         for p, g in zip(self._params(), self.grads):

@@ -5,7 +5,9 @@ cameras and all-reduce the flat gradient buffer == one rank accumulating the gra
 
 Checks, for C cameras sharded round-robin: (a) eager render() + dist.allreduce_splat_grads, (b) the same step replayed
 as a CUDA graph with the NCCL all-reduce captured inside, (c) the NVLS multimem.red path (SymmetricGradBuffer) when the
-fabric offers multicast, (d) the two-shot NVLS all-reduce kernel (csrc/nvls.cu), eager and captured inside the graph.  Rank 0 prints one JSON line and exits non-zero on a mismatch."""
+fabric offers multicast, (d) the two-shot NVLS all-reduce kernel (csrc/nvls.cu), eager and captured inside the graph,
+(e) the deferred reduction: two graphs / two gradient buffers used alternately, each graph all-reducing the other's
+buffer on a forked branch (graph.pair_with_deferred_reduce), with the NVLS kernel and with NCCL.  Rank 0 prints one JSON line and exits non-zero on a mismatch."""
 import json
 import math
 import os
@@ -17,7 +19,7 @@ import torch.distributed as dist
 
 from gaussianavatars_b200 import dist as gdist
 from gaussianavatars_b200 import synthetic as syn
-from gaussianavatars_b200.graph import GraphedFrame, camera_block
+from gaussianavatars_b200.graph import GraphedFrame, camera_block, pair_with_deferred_reduce, reduced_grads
 from gaussianavatars_b200.model import MeshBoundGaussians
 from gaussianavatars_b200.renderer import render
 
@@ -122,6 +124,10 @@ def main():
             assert symm.end(), "the symmetric buffer was not used"
             acc += torch.cat([p.grad.reshape(-1) for p in pc.parameters()])
         out["nvls2_eager"] = float((acc - ref).abs().max()) / scale
+        del o                                  # the eager autograd graph must be gone before the model is captured
+        pc = model()
+        symm = gdist.SymmetricGradBuffer(pc, mode="two_shot")
+        pc.symm_grad = symm
         fr2 = GraphedFrame(pc, W, H, cams[0].FoVx, cams[0].FoVy, bg, loss="dL_dimage",
                            warm_cameras=[camera_block(cams[i]).to(dev) for i in mine],
                            before_backward=symm.begin, after_backward=symm.end)
@@ -137,8 +143,40 @@ def main():
             out["nvls2_graph"] = 1.0
     else:
         out["nvls2_eager"] = out["nvls2_graph"] = None
+    # (e) deferred reduction: the reduced gradients of step j are read after replay j+1 (the last ones after reduce())
+    for mode in ("two_shot", "plain"):
+        pc = model()
+        bufs = [gdist.SymmetricGradBuffer(pc, mode=mode) for _ in range(2)]
+        if not all(b.enabled for b in bufs):
+            out[f"deferred_{mode}"] = None
+            continue
+        pair = []
+        for k in range(2):
+            f = GraphedFrame(pc, W, H, cams[0].FoVx, cams[0].FoVy, bg, loss="dL_dimage",
+                             warm_cameras=[camera_block(cams[i]).to(dev) for i in mine])
+            f.set_inputs(camera=camera_block(cams[mine[0]]).to(dev), verts=pc.verts_rest, dL_dimage=gout)
+            pair.append(f)
+        pair_with_deferred_reduce(pair, bufs)
+        for f in pair:
+            f.capture()
+        acc = torch.zeros_like(ref)
+        order = list(mine) + list(mine) + list(mine)[:1]       # odd number of steps: both frames end up draining
+        for j, i in enumerate(order):
+            k = j % 2
+            pair[k].set_inputs(camera=camera_block(cams[i]).to(dev), verts=syn.pose_mesh(pc.verts_rest, cams[i].timestep))
+            pair[k].run()
+            if j > 0:
+                acc += torch.cat([g.reshape(-1) for g in reduced_grads(bufs, k)])
+        k = (len(order) - 1) % 2
+        bufs[k].reduce()
+        acc += torch.cat([g.reshape(-1) for g in bufs[k].all_views[0]])
+        assert not any(f.overflowed(wait=True) for f in pair)
+        # every rank stepped through its cameras twice plus its first camera once more
+        want = 2 * ref + sum(frame_grads(model(), cams[r]) for r in range(world))
+        out[f"deferred_{mode}"] = float((acc - want).abs().max()) / scale
     t = torch.tensor([max(v for k, v in out.items()
-                          if k in ("eager_nccl", "graph_nccl", "nvls_multimem", "nvls2_eager", "nvls2_graph") and v is not None)],
+                          if k in ("eager_nccl", "graph_nccl", "nvls_multimem", "nvls2_eager", "nvls2_graph",
+                                   "deferred_two_shot", "deferred_plain") and v is not None)],
                      device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ok = float(t) < 2e-5

@@ -108,3 +108,65 @@ def test_two_rank_sharded_grads_equal_single_rank_accumulation(tmp_path):
     for i, p in enumerate(ref.values()):
         a, b = got[f"g{i}"].reshape(-1), p.grad.numpy().reshape(-1)
         assert np.allclose(a, b, rtol=1e-4, atol=1e-6 * np.abs(b).max()), f"param {i}"
+
+
+class _Model:
+    """Six parameters laid out like the fused backward's flat buffer (widths 3 + 3 + 45 + 1 + 3 + 4 = 59)."""
+
+    def __init__(self, P):
+        self.ps = [torch.nn.Parameter(torch.zeros(P, w)) for w in (3, 3, 45, 1, 3, 4)]
+
+    def parameters(self):
+        return self.ps
+
+
+def _fill(buf, pc, value):
+    """What the fused backward does with a caller-owned buffer: store the step's local gradients, flag the model."""
+    buf.flat.fill_(value)
+    pc._gab200_mc_used = True
+
+
+def _deferred_worker(rank, world, port):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from gaussianavatars_b200 import dist as gdist
+
+    pc = _Model(7)
+    bufs = [gdist.SymmetricGradBuffer(pc, mode="plain") for _ in range(2)]
+    assert all(b.enabled and b.numel == 7 * 59 for b in bufs)
+    total = sum(range(1, world + 1))
+    # synchronous protocol: begin / backward / end
+    bufs[0].begin()
+    _fill(bufs[0], pc, float(rank + 1))
+    assert bufs[0].end() is True
+    assert all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(pc.parameters(), bufs[0].all_views[0]))
+    assert torch.all(pc.parameters()[2].grad == total)
+    # deferred: step j fills buffer j % 2 and adopts the LOCAL gradients; the other buffer is reduced "meanwhile"
+    seen = []
+    for j in range(5):
+        k = j % 2
+        bufs[k].begin()
+        _fill(bufs[k], pc, float((rank + 1) * 10 ** j))
+        assert bufs[k].end(reduce=False) is True
+        assert torch.all(pc.parameters()[0].grad == (rank + 1) * 10 ** j)      # local, unreduced
+        if j > 0:
+            bufs[1 - k].reduce()                                              # the previous step's gradients
+            seen.append(float(bufs[1 - k].all_views[0][5][0, 0]))
+    bufs[4 % 2].reduce()
+    seen.append(float(bufs[0].all_views[0][5][0, 0]))
+    assert seen == [float(total * 10 ** j) for j in range(5)], seen
+    # a model whose parameters were replaced (densification): the buffer refuses, the fallback all-reduce takes over
+    pc.ps[0] = torch.nn.Parameter(torch.zeros(7, 3))
+    for p in pc.parameters():
+        p.grad = torch.full_like(p, float(rank + 1))
+    bufs[0].begin()
+    pc._gab200_mc_used = True
+    assert bufs[0].end() is False and not bufs[0].matches()
+    assert torch.all(pc.parameters()[0].grad == total)
+    dist.destroy_process_group()
+
+
+def test_caller_owned_gradient_buffer_sync_and_deferred_reduction():
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_deferred_worker, args=(2, port), nprocs=2, join=True)
