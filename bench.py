@@ -507,8 +507,7 @@ def main():
             step_resident(i)
         barrier()
         ms_sync, _, _, _, _, _ = timed_pass(step_resident, False)
-        sync_line = {"value": world * K / (ms_sync / 1e3), "unit": "frames/s", "ms_per_step": ms_sync / K,
-                     "what": "collective after backward inside the same graph (on the critical path)"}
+        sync_line = ms_sync   # max over ranks below
         pair, why = capture_agreed(build_deferred)
         if pair is None:
             graph_note = f"deferred-reduction pair not capturable ({why}); synchronous step timed"
@@ -675,8 +674,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    per_rank = None
+    if world > 1:   # every rank's own clock over the same K steps: skew between ranks is part of a max-over-ranks metric
+        mine_t = torch.tensor([ms_total / K, ms_eager / K, ms_e2e / K, float(len(my_cams))], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(mine_t) for _ in range(world)]
+        dist.all_gather(allt, mine_t)
+        per_rank = {"ms_per_step": [round(float(t[0]), 4) for t in allt], "eager_ms_per_step": [round(float(t[1]), 4) for t in allt],
+                    "e2e_ms_per_step": [round(float(t[2]), 4) for t in allt], "cameras": [int(t[3]) for t in allt]}
     ms_total, ms_warm, ms_e2e = max_over_ranks(ms_total), max_over_ranks(ms_warm), max_over_ranks(ms_e2e)
     ms_eager, ms_instrumented = max_over_ranks(ms_eager), max_over_ranks(ms_instrumented)
+    if sync_line is not None:
+        ms_sync = max_over_ranks(sync_line)
+        sync_line = {"value": world * K / (ms_sync / 1e3), "unit": "frames/s", "ms_per_step": ms_sync / K,
+                     "what": "collective after backward inside the same graph (on the critical path)"}
     if rank != 0:
         finish(world, dev)
         return
@@ -737,6 +747,7 @@ def main():
                 "path": ("two GraphedFrame(host_inputs=True, loss='l1_u8') prefetching each other's inputs from pinned "
                          "staging inside their graphs") if use_graph else "eager render() + l1_loss_u8"},
         **({"sync_collective": sync_line} if sync_line else {}),
+        **({"per_rank": per_rank} if per_rank else {}),
         "gpu_launches": int(launches),
         "graph_overflow": bool(overflow_steps),
         "clocks": clk.summary(),
