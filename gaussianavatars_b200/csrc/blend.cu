@@ -26,6 +26,7 @@
 //     tile (8 STS + 2 LDS.128 + 2 shuffles), the ninth takes 5 shuffles, and they leave the SM as ONE 9-lane
 //     RED.ADD.F32 pair per (warp, splat).
 // Tensor cores are not used: there is no dense contraction on this path (north_star).
+#include <type_traits>
 #include "common.cuh"
 #include "kernels.cuh"
 
@@ -127,9 +128,10 @@ struct BandGeom {
 // =====================================================================================================
 template <int K>
 __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
-                                             SplatRec* buf1, uint32_t* smask, uint32_t* ids_ring, uint64_t* mbar,
-                                             int W, int H, int gx,
+                                             SplatRec* buf1, uint32_t* smask, uint32_t* ids_ring, uint32_t* keys_ring,
+                                             uint64_t* mbar, int W, int H, int gx,
                                              const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
+                                             const uint32_t* __restrict__ inst_keys,
                                              const SplatRec* __restrict__ rec, const float* __restrict__ bg,
                                              float* __restrict__ out_color, float* __restrict__ final_T,
                                              uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ strip_mask) {
@@ -147,6 +149,9 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   const int n = (int)(range.y - range.x);
   const uint32_t* ids = point_list + range.x;
   const bool want_mask = strip_mask != nullptr;
+  // per-instance block masks from the emission (high byte of the sorted key, kernels.cuh): a splat whose mask has no
+  // bit of this warp's blocks cannot reach alpha >= 1/255 on any of the warp's pixels and is skipped unevaluated
+  const bool have_geo = inst_keys != nullptr;
   smask[tl] = 0;
 
   float T[K], Cr[K], Cg[K], Cb[K];
@@ -167,6 +172,7 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   constexpr uint32_t CHUNK_BYTES = RING_STRIDE * 4;
   const int mis = (int)(range.x & 3u);
   const uint32_t* ids_al = ids - mis;
+  const uint32_t* keys_al = have_geo ? inst_keys + range.x - mis : nullptr;
   if (tl == 0) {
 #pragma unroll
     for (int k = 0; k < ID_RING; k++) mbar_init(&mbar[k], 1);
@@ -175,8 +181,9 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   bar.sync();
   auto issue_ids = [&](int k) {  // one thread: arm the barrier with the byte count, start the copy
     uint64_t* b = &mbar[k % ID_RING];
-    mbar_arrive_expect_tx(b, CHUNK_BYTES);
+    mbar_arrive_expect_tx(b, have_geo ? 2 * CHUNK_BYTES : CHUNK_BYTES);
     bulk_copy_g2s(ids_ring + (k % ID_RING) * RING_STRIDE, ids_al + (size_t)k * NT, CHUNK_BYTES, b);
+    if (have_geo) bulk_copy_g2s(keys_ring + (k % ID_RING) * RING_STRIDE, keys_al + (size_t)k * NT, CHUNK_BYTES, b);
   };
   auto wait_ids = [&](int k) { mbar_wait(&mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1)); };
   if (tl == 0) {
@@ -214,12 +221,22 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
     uint32_t lb[K];
 #pragma unroll
     for (int i = 0; i < K; i++) lb[i] = 0;
+    // this warp's block bits inside the key's mask byte
+    uint32_t mybits = 0;
+#pragma unroll
+    for (int i = 0; i < K; i++) mybits |= 1u << (GAB_KEY_BLOCKS_SHIFT + geo.bit(i));
+    const uint32_t* kr = keys_ring + (c % ID_RING) * RING_STRIDE + mis;
     // 32-splat groups: the inner loop is branch-light and unrolled; the per-group epilogue publishes the strip bits
     // and tests saturation once per group
     for (int gbase = 0; gbase < cnt; gbase += 32) {
       const int gend = min(32, cnt - gbase);
 #pragma unroll 4
       for (int jj = 0; jj < gend; jj++) {
+        uint32_t gm = 0xffffffffu;
+        if (have_geo) {
+          gm = kr[gbase + jj];
+          if (!(gm & mybits)) continue;   // warp-uniform: the whole warp shares its blocks
+        }
         const SplatRec* r = cur + gbase + jj;
         const float4 q0 = r->q0;
         const float4 q1 = r->q1;
@@ -227,6 +244,7 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
         const float tA = q0.z * dx;  // conic pre-scaled by preprocess: pw = A' dx^2 + B' dx dy + C' dy^2 (log2 units)
 #pragma unroll
         for (int i = 0; i < K; i++) {
+          if (K > 1 && !((gm >> (GAB_KEY_BLOCKS_SHIFT + geo.bit(i))) & 1u)) continue;
           const float dy = q0.y - fy[i];
           const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
           const float alpha = fminf(0.99f, q1.y * ex2_approx(pw));
@@ -296,10 +314,12 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
                                                             const float* __restrict__ bg, float* __restrict__ out_color,
                                                             float* __restrict__ final_T,
                                                             uint32_t* __restrict__ n_contrib,
-                                                            uint8_t* __restrict__ strip_mask) {
+                                                            uint8_t* __restrict__ strip_mask,
+                                                            const uint32_t* __restrict__ inst_keys) {
   __shared__ SplatRec buf[2][256];
   __shared__ uint32_t smask[256];
   __shared__ __align__(16) uint32_t ids_ring[4][ID_RING * (64 + 4)];  // per 64-thread group; a 256-thread tile uses it flat
+  __shared__ __align__(16) uint32_t keys_ring[4][ID_RING * (64 + 4)];
   __shared__ __align__(8) uint64_t mbar[4][ID_RING];
   constexpr int GH = KH;  // heavy tiles per CTA (256/KH threads each)
   constexpr int NTH = 256 / KH;
@@ -310,27 +330,29 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
     const int g = t / NTH, slot = b * GH + g;
     if (slot >= nh) return;
     forward_tile<KH>((int)order[slot], t - g * NTH, GroupBarrier<NTH>{GH == 1 ? 0 : 1 + g}, buf[0] + g * NTH,
-                     buf[1] + g * NTH, smask + g * NTH, &ids_ring[0][0] + g * (ID_RING * (NTH + 4)), mbar[g], W, H, gx,
-                     ranges, point_list, rec, bg, out_color, final_T, n_contrib, strip_mask);
+                     buf[1] + g * NTH, smask + g * NTH, &ids_ring[0][0] + g * (ID_RING * (NTH + 4)),
+                     &keys_ring[0][0] + g * (ID_RING * (NTH + 4)), mbar[g], W, H, gx, ranges, point_list, inst_keys, rec,
+                     bg, out_color, final_T, n_contrib, strip_mask);
   } else {
     const int g = t >> 6, slot = nh + 4 * (b - heavy_ctas) + g;
     if (slot >= tiles) return;
     forward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
-                    smask + g * 64, ids_ring[g], mbar[g], W, H, gx, ranges, point_list, rec, bg, out_color, final_T,
-                    n_contrib, strip_mask);
+                    smask + g * 64, ids_ring[g], keys_ring[g], mbar[g], W, H, gx, ranges, point_list, inst_keys, rec, bg,
+                    out_color, final_T, n_contrib, strip_mask);
   }
 }
 
 void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
                           const uint32_t* point_list, const SplatRec* rec, const float* bg, float* out_color,
-                          float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, cudaStream_t stream) {
+                          float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, const uint32_t* inst_keys,
+                          cudaStream_t stream) {
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
   // upper bound on CTAs: every tile heavy; surplus CTAs exit at once
   const int grid = tiles;
   blend_forward_kernel<1><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
-                                                    out_color, final_T, n_contrib, strip_mask);
+                                                    out_color, final_T, n_contrib, strip_mask, inst_keys);
   count_launch();
 }
 
@@ -373,6 +395,141 @@ struct PixState {
 };
 struct SplatSums {  // per-lane sums over the lane's pixels for one splat
   float S0, S1, S2, go, gr, gg, gb;
+};
+
+// ---- packed fp32 pairs ----------------------------------------------------------------------------------------
+// sm_100 executes FFMA2 / FMUL2 / FADD2 on a 64-bit register pair (PTX fma.rn.f32x2 ...): two IEEE fp32 operations,
+// each rounded exactly like its scalar form, in ONE issue slot and ONE pass through the fma pipe, with negation and
+// scalar-broadcast operand modifiers.  The scalar 3-register FFMA occupies the pipe for two cycles per warp
+// (B300_MICROARCH.md: rt_SMSP = 2), which is what bounded both blend kernels (profiles/r02/ncu_blend_final_summary.csv:
+// 152 of 246 loop instructions of the backward were scalar FFMA/FMUL/FADD = 304 of its 346 cycles per visit).  The
+// two bands of a pair run the same straight-line arithmetic, so their state lives in float2 and the math is packed.
+typedef float2 v2;
+__device__ __forceinline__ v2 bc2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ v2 neg2(v2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ v2 add2(v2 a, v2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ v2 mul2(v2 a, v2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ v2 fma2(v2 a, v2 b, v2 c) { return __ffma2_rn(a, b, c); }
+
+// element i of a per-band array, whichever way it is stored
+__device__ __forceinline__ float& el(float* a, int i) { return a[i]; }
+__device__ __forceinline__ int& el(int* a, int i) { return a[i]; }
+__device__ __forceinline__ float& el(v2* a, int i) { return (i & 1) ? a[i >> 1].y : a[i >> 1].x; }
+
+// The same state with bands (2J, 2J+1) paired in float2 registers.
+template <int K>
+struct PixState2 {
+  v2 fy[K / 2], T[K / 2];
+  v2 ar[K / 2], ag[K / 2], ab[K / 2];
+  v2 dr[K / 2], dg[K / 2], db[K / 2];
+  v2 bgT[K / 2];
+  int nc[K];
+};
+struct SplatSums2 {  // (even band, odd band) partial sums, added at the end of the visit
+  v2 S0, S1, S2, go, gr, gg, gb;
+};
+// Bands 2J and 2J+1 of one visit, both live: visit_bands' arithmetic, element for element, two bands per instruction.
+template <int K, int J>
+__device__ __forceinline__ void visit_pair(PixState2<K>& p, int pos, float py, float tA, float dx, float Bp, float Cp,
+                                           float op, float cr, float cg, float cb, SplatSums2& s) {
+  const v2 dy = add2(bc2(py), neg2(p.fy[J]));
+  const v2 pw = fma2(mul2(bc2(Cp), dy), dy, mul2(fma2(bc2(Bp), dy, bc2(tA)), bc2(dx)));  // the forward's expression
+  const v2 G = make_float2(ex2_approx(pw.x), ex2_approx(pw.y));
+  const v2 a = mul2(bc2(op), G);
+  const v2 alpha = make_float2(fminf(0.99f, a.x), fminf(0.99f, a.y));
+  const bool vx = pos < p.nc[2 * J] && pw.x <= 0.f && alpha.x >= ALPHA_MIN;
+  const bool vy = pos < p.nc[2 * J + 1] && pw.y <= 0.f && alpha.y >= ALPHA_MIN;
+  const v2 om = add2(bc2(1.f), neg2(alpha));
+  const v2 al = make_float2(vx ? alpha.x : 0.f, vy ? alpha.y : 0.f);
+  const v2 Gv = make_float2(vx ? G.x : 0.f, vy ? G.y : 0.f);
+  const v2 ra = make_float2(vx ? rcp_approx(om.x) : 1.f, vy ? rcp_approx(om.y) : 1.f);
+  const v2 Tn = mul2(p.T[J], ra);
+  p.T[J] = Tn;
+  const v2 w = mul2(al, Tn);
+  s.gr = fma2(w, p.dr[J], s.gr);
+  s.gg = fma2(w, p.dg[J], s.gg);
+  s.gb = fma2(w, p.db[J], s.gb);
+  const v2 er = add2(bc2(cr), neg2(p.ar[J])), eg = add2(bc2(cg), neg2(p.ag[J])), eb = add2(bc2(cb), neg2(p.ab[J]));
+  v2 dLda = mul2(er, p.dr[J]);
+  dLda = fma2(eg, p.dg[J], dLda);
+  dLda = fma2(eb, p.db[J], dLda);
+  dLda = fma2(dLda, Tn, neg2(mul2(p.bgT[J], ra)));
+  p.ar[J] = fma2(al, er, p.ar[J]);
+  p.ag[J] = fma2(al, eg, p.ag[J]);
+  p.ab[J] = fma2(al, eb, p.ab[J]);
+  const v2 t = mul2(Gv, dLda);
+  s.go = add2(s.go, t);
+  const v2 s_ = mul2(bc2(op), t);
+  const v2 sd = mul2(s_, dy);
+  s.S0 = add2(s.S0, s_);
+  s.S1 = add2(s.S1, sd);
+  s.S2 = fma2(sd, dy, s.S2);
+}
+// One live band I of a pair-stored state (the other band of its pair is dead for this splat): scalar arithmetic on
+// the band's half of the registers, sums into the matching half of the accumulators.
+template <int K, int I>
+__device__ __forceinline__ void visit_single(PixState2<K>& p, int pos, float py, float tA, float dx, float Bp, float Cp,
+                                             float op, float cr, float cg, float cb, SplatSums2& s) {
+  const float dy = py - el(p.fy, I);
+  const float pw = fmaf(Cp * dy, dy, fmaf(Bp, dy, tA) * dx);
+  const float G = ex2_approx(pw);
+  const float alpha = fminf(0.99f, op * G);
+  const bool valid = pos < p.nc[I] && pw <= 0.f && alpha >= ALPHA_MIN;
+  const float al = valid ? alpha : 0.f;
+  const float Gv = valid ? G : 0.f;
+  const float ra = valid ? rcp_approx(1.f - alpha) : 1.f;
+  const float Tn = el(p.T, I) * ra;
+  el(p.T, I) = Tn;
+  const float w = al * Tn;
+  const float dr = el(p.dr, I), dg = el(p.dg, I), db = el(p.db, I);
+  el(&s.gr, I & 1) = fmaf(w, dr, el(&s.gr, I & 1));
+  el(&s.gg, I & 1) = fmaf(w, dg, el(&s.gg, I & 1));
+  el(&s.gb, I & 1) = fmaf(w, db, el(&s.gb, I & 1));
+  const float er = cr - el(p.ar, I), eg = cg - el(p.ag, I), eb = cb - el(p.ab, I);
+  float dLda = er * dr;
+  dLda = fmaf(eg, dg, dLda);
+  dLda = fmaf(eb, db, dLda);
+  dLda = fmaf(dLda, Tn, -el(p.bgT, I) * ra);
+  el(p.ar, I) = fmaf(al, er, el(p.ar, I));
+  el(p.ag, I) = fmaf(al, eg, el(p.ag, I));
+  el(p.ab, I) = fmaf(al, eb, el(p.ab, I));
+  const float t = Gv * dLda;
+  el(&s.go, I & 1) += t;
+  const float s_ = op * t;
+  const float sd = s_ * dy;
+  el(&s.S0, I & 1) += s_;
+  el(&s.S1, I & 1) += sd;
+  el(&s.S2, I & 1) = fmaf(sd, dy, el(&s.S2, I & 1));
+}
+// pairs one after the other; a pair with one live band takes the scalar form, a dead pair is skipped (uniform branches)
+template <int K, int J>
+struct PairLoop {
+  static __device__ __forceinline__ void run(uint32_t m, PixState2<K>& p, int pos, float py, float tA, float dx, float Bp,
+                                             float Cp, float op, float cr, float cg, float cb, SplatSums2& s) {
+    const uint32_t mm = (m >> (2 * J)) & 3u;
+    if (mm == 3u) visit_pair<K, J>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+    else if (mm == 1u) visit_single<K, 2 * J>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+    else if (mm == 2u) visit_single<K, 2 * J + 1>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+    PairLoop<K, J + 1>::run(m, p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+  }
+};
+template <int K>
+struct PairLoop<K, K / 2> {
+  static __device__ __forceinline__ void run(uint32_t, PixState2<K>&, int, float, float, float, float, float, float, float,
+                                             float, float, SplatSums2&) {}
+};
+template <int K, int J>
+struct PairAll {  // every band live: all pairs packed, straight line
+  static __device__ __forceinline__ void run(PixState2<K>& p, int pos, float py, float tA, float dx, float Bp, float Cp,
+                                             float op, float cr, float cg, float cb, SplatSums2& s) {
+    visit_pair<K, J>(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+    PairAll<K, J + 1>::run(p, pos, py, tA, dx, Bp, Cp, op, cr, cg, cb, s);
+  }
+};
+template <int K>
+struct PairAll<K, K / 2> {
+  static __device__ __forceinline__ void run(PixState2<K>&, int, float, float, float, float, float, float, float, float,
+                                             float, SplatSums2&) {}
 };
 
 // One (splat, warp) visit restricted to the live bands M (compile-time set): straight-line code, the bands'
@@ -655,6 +812,7 @@ __device__ __forceinline__ void backward_tile(int tile, int tl, GroupBarrier<256
 #define BANDS_UNIFORM 2   // each band under a warp-uniform branch (dead bands skipped, no interleaving)
 #define BANDS_HYBRID 3    // all bands live: straight-line; otherwise as BANDS_UNIFORM
 #define BANDS_SWITCH 4    // one straight-line body per live-band set (visit_switch)
+#define BANDS_PACKED 5    // as BANDS_HYBRID with the bands of a pair in packed fp32x2 arithmetic (FFMA2/FMUL2/FADD2)
 
 #define ROWS_STRIDE 36
 #define ROWS_WORDS (9 * ROWS_STRIDE)
@@ -686,24 +844,29 @@ __device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, in
   const size_t HW = (size_t)H * W;
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
 
-  PixState<K> p;
+  constexpr bool PACKED = (MODE == BANDS_PACKED);
+  typename std::conditional<PACKED, PixState2<K>, PixState<K>>::type p;
   int n = 0;
 #pragma unroll
   for (int i = 0; i < K; i++) {
     const int y = pixy0 + 4 * i;
-    p.fy[i] = (float)y;
-    p.ar[i] = p.ag[i] = p.ab[i] = 0.f;
+    el(p.fy, i) = (float)y;
+    el(p.ar, i) = el(p.ag, i) = el(p.ab, i) = 0.f;
+    float T0 = 0.f, dr = 0.f, dg = 0.f, db = 0.f;
+    p.nc[i] = 0;
     if (pixx < W && y < H) {
       const size_t pix = (size_t)y * W + pixx;
-      p.T[i] = final_T[pix];
+      T0 = final_T[pix];
       p.nc[i] = (int)n_contrib[pix];
-      p.dr[i] = dL_dpix[pix];
-      p.dg[i] = dL_dpix[HW + pix];
-      p.db[i] = dL_dpix[2 * HW + pix];
-    } else {
-      p.T[i] = 0.f; p.nc[i] = 0; p.dr[i] = p.dg[i] = p.db[i] = 0.f;
+      dr = dL_dpix[pix];
+      dg = dL_dpix[HW + pix];
+      db = dL_dpix[2 * HW + pix];
     }
-    p.bgT[i] = p.T[i] * (bg0 * p.dr[i] + bg1 * p.dg[i] + bg2 * p.db[i]);
+    el(p.T, i) = T0;
+    el(p.dr, i) = dr;
+    el(p.dg, i) = dg;
+    el(p.db, i) = db;
+    el(p.bgT, i) = T0 * (bg0 * dr + bg1 * dg + bg2 * db);
     n = max(n, p.nc[i]);
   }
   // this warp only needs instances [0, max n_contrib of ITS pixels)
@@ -766,8 +929,17 @@ __device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, in
     const float4* r4 = reinterpret_cast<const float4*>(&sm.rows[par ^ 1][c1 * ROWS_STRIDE + h1 * 16]);
     const float4 a = r4[0], b = r4[1], c = r4[2], d = r4[3];
     if (id_part != 0xffffffffu && lane < 9) atomicAdd(g2d + (size_t)id_part * GAB_G2D_STRIDE + lane, pp.x + pp.y);
-    const float s = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
-                    (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    float s;
+    if constexpr (PACKED) {  // 7 packed adds + 1 instead of 15
+      const v2 u = add2(add2(add2(make_float2(a.x, a.y), make_float2(a.z, a.w)),
+                             add2(make_float2(b.x, b.y), make_float2(b.z, b.w))),
+                        add2(add2(make_float2(c.x, c.y), make_float2(c.z, c.w)),
+                             add2(make_float2(d.x, d.y), make_float2(d.z, d.w))));
+      s = u.x + u.y;
+    } else {
+      s = (((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w))) +
+          (((c.x + c.y) + (c.z + c.w)) + ((d.x + d.y) + (d.z + d.w)));
+    }
     if (id_rows != 0xffffffffu && lane < 18) sm.part[par ^ 1][lane] = s;
   };
 
@@ -795,7 +967,14 @@ __device__ __forceinline__ void backward_task(int tile, int tl, WarpSmem& sm, in
       const float tA = q0.z * dx;
       SplatSums s;
       s.S0 = s.S1 = s.S2 = s.go = s.gr = s.gg = s.gb = 0.f;
-      if (MODE == BANDS_ALWAYS || (MODE == BANDS_HYBRID && m == (1u << K) - 1u)) {
+      if constexpr (PACKED) {
+        SplatSums2 s2;
+        s2.S0 = s2.S1 = s2.S2 = s2.go = s2.gr = s2.gg = s2.gb = make_float2(0.f, 0.f);
+        if (m == (1u << K) - 1u) PairAll<K, 0>::run(p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s2);
+        else PairLoop<K, 0>::run(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s2);
+        s.S0 = s2.S0.x + s2.S0.y; s.S1 = s2.S1.x + s2.S1.y; s.S2 = s2.S2.x + s2.S2.y; s.go = s2.go.x + s2.go.y;
+        s.gr = s2.gr.x + s2.gr.y; s.gg = s2.gg.x + s2.gg.y; s.gb = s2.gb.x + s2.gb.y;
+      } else if (MODE == BANDS_ALWAYS || (MODE == BANDS_HYBRID && m == (1u << K) - 1u)) {
         visit_bands<K, (1 << K) - 1>(p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
       } else if (MODE == BANDS_SWITCH) {
         visit_switch<K>(m, p, pos, q0.y, tA, dx, q0.w, q1.x, q1.y, q1.z, q1.w, cbl, s);
@@ -920,6 +1099,8 @@ void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* or
     case 5: GAB_BWD_WARP(BANDS_UNIFORM, 5); break;
     case 6: GAB_BWD_WARP(BANDS_SWITCH, 4); break;
     case 7: GAB_BWD_WARP(BANDS_UNIFORM, 6); break;
+    case 8: GAB_BWD_WARP(BANDS_PACKED, 4); break;
+    case 9: GAB_BWD_WARP(BANDS_PACKED, 5); break;
     default:
       blend_backward_kernel<<<tiles, 128, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
                                                        final_T, n_contrib, dL_dpix, strip_mask, g2d);

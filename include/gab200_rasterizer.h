@@ -435,6 +435,8 @@ enum {
                                   size the counting form is SLOWER (same-address atomics on the hot tiles' counters:
                                   preprocess +18 us, emission 26 -> 78 us; profiles/r02/tile_sort_counting_vs_cub.json) */
   GAB200_TUNE_NVLS_CTAS = 5,   /* gab200_nvls_allreduce: CTAs of 256 threads (0 = default: 64) */
+  GAB200_TUNE_FWD_BLOCKS = 6,  /* forward blend: 1 (default) skip the (splat, 8x4-pixel block) pairs the emission proved empty
+                                  (block mask in the high byte of the sorted instance key); 0 evaluate every pair */
   GAB200_NUM_TUNABLES = 8
 };
 int32_t gab200_tune(int32_t knob, int32_t value);

@@ -21,3 +21,18 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _tune_from_env():
+    """GAB200_TEST_TUNE="3=8,6=1": run the whole suite with library tuning knobs (include/gab200_rasterizer.h
+    GAB200_TUNE_*) set to non-default values -- how a candidate kernel variant is put through every parity test before
+    it becomes the default."""
+    spec = os.environ.get("GAB200_TEST_TUNE", "")
+    if spec:
+        from gaussianavatars_b200 import _native as N
+
+        for kv in spec.split(","):
+            k, v = kv.split("=")
+            N.tune(int(k), int(v))
+    yield
