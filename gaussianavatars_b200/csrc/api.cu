@@ -220,7 +220,7 @@ static int check_arch() {
 
 // tuning knobs (gab200_tune)
 static std::atomic<int> g_tune[GAB200_NUM_TUNABLES];
-static const int g_tune_default[GAB200_NUM_TUNABLES] = {32, 2048, 0, 8, 0, 0, 1, 0};  // see GAB200_TUNE_*
+static const int g_tune_default[GAB200_NUM_TUNABLES] = {32, 2048, 0, 8, 0, 0, 0, 0};  // see GAB200_TUNE_*
 int tune_get(int knob) {
   const int v = g_tune[knob].load(std::memory_order_relaxed);
   return v > 0 ? v - 1 : g_tune_default[knob];  // stored biased by one so that zero-initialised = "default"
@@ -477,11 +477,8 @@ int enqueue_binning_blend(Frame& f, void* bin, int64_t cap, int64_t n_known, siz
   st->sorted_selector = selector;
   {
     StageScope sc(GAB200_STAGE_BLEND_FWD, stream);
-    // the sorted keys carry the emission's block masks in their high byte (cub path; the counting sort's keys are
-    // depth ranks) -- GAB200_TUNE_FWD_BLOCKS = 0 makes the forward ignore them
-    const uint32_t* inst_keys = (!counting && n_sort > 0 && tune_get(GAB200_TUNE_FWD_BLOCKS) != 0) ? bv.keys[selector] : nullptr;
     launch_blend_forward(f.W, f.H, f.iv.ranges, f.iv.order, f.iv.order_info, bv.vals[selector], f.g.rec, a->bg,
-                         a->out_color, f.iv.final_T, f.iv.n_contrib, bv.strip_mask, inst_keys, stream);
+                         a->out_color, f.iv.final_T, f.iv.n_contrib, bv.strip_mask, stream);
   }
   GAB_STAGE_CHECK(f.dbg, stream);
   return GAB200_OK;

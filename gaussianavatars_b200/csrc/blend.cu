@@ -128,10 +128,9 @@ struct BandGeom {
 // =====================================================================================================
 template <int K>
 __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 / K> bar, SplatRec* buf0,
-                                             SplatRec* buf1, uint32_t* smask, uint32_t* ids_ring, uint32_t* keys_ring,
-                                             uint64_t* mbar, int W, int H, int gx,
+                                             SplatRec* buf1, uint32_t* smask, uint32_t* ids_ring, uint64_t* mbar,
+                                             int W, int H, int gx,
                                              const uint2* __restrict__ ranges, const uint32_t* __restrict__ point_list,
-                                             const uint32_t* __restrict__ inst_keys,
                                              const SplatRec* __restrict__ rec, const float* __restrict__ bg,
                                              float* __restrict__ out_color, float* __restrict__ final_T,
                                              uint32_t* __restrict__ n_contrib, uint8_t* __restrict__ strip_mask) {
@@ -149,9 +148,6 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   const int n = (int)(range.y - range.x);
   const uint32_t* ids = point_list + range.x;
   const bool want_mask = strip_mask != nullptr;
-  // per-instance block masks from the emission (high byte of the sorted key, kernels.cuh): a splat whose mask has no
-  // bit of this warp's blocks cannot reach alpha >= 1/255 on any of the warp's pixels and is skipped unevaluated
-  const bool have_geo = inst_keys != nullptr;
   smask[tl] = 0;
 
   float T[K], Cr[K], Cg[K], Cb[K];
@@ -172,7 +168,6 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   constexpr uint32_t CHUNK_BYTES = RING_STRIDE * 4;
   const int mis = (int)(range.x & 3u);
   const uint32_t* ids_al = ids - mis;
-  const uint32_t* keys_al = have_geo ? inst_keys + range.x - mis : nullptr;
   if (tl == 0) {
 #pragma unroll
     for (int k = 0; k < ID_RING; k++) mbar_init(&mbar[k], 1);
@@ -181,9 +176,8 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
   bar.sync();
   auto issue_ids = [&](int k) {  // one thread: arm the barrier with the byte count, start the copy
     uint64_t* b = &mbar[k % ID_RING];
-    mbar_arrive_expect_tx(b, have_geo ? 2 * CHUNK_BYTES : CHUNK_BYTES);
+    mbar_arrive_expect_tx(b, CHUNK_BYTES);
     bulk_copy_g2s(ids_ring + (k % ID_RING) * RING_STRIDE, ids_al + (size_t)k * NT, CHUNK_BYTES, b);
-    if (have_geo) bulk_copy_g2s(keys_ring + (k % ID_RING) * RING_STRIDE, keys_al + (size_t)k * NT, CHUNK_BYTES, b);
   };
   auto wait_ids = [&](int k) { mbar_wait(&mbar[k % ID_RING], (uint32_t)((k / ID_RING) & 1)); };
   if (tl == 0) {
@@ -221,22 +215,12 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
     uint32_t lb[K];
 #pragma unroll
     for (int i = 0; i < K; i++) lb[i] = 0;
-    // this warp's block bits inside the key's mask byte
-    uint32_t mybits = 0;
-#pragma unroll
-    for (int i = 0; i < K; i++) mybits |= 1u << (GAB_KEY_BLOCKS_SHIFT + geo.bit(i));
-    const uint32_t* kr = keys_ring + (c % ID_RING) * RING_STRIDE + mis;
     // 32-splat groups: the inner loop is branch-light and unrolled; the per-group epilogue publishes the strip bits
     // and tests saturation once per group
     for (int gbase = 0; gbase < cnt; gbase += 32) {
       const int gend = min(32, cnt - gbase);
 #pragma unroll 4
       for (int jj = 0; jj < gend; jj++) {
-        uint32_t gm = 0xffffffffu;
-        if (have_geo) {
-          gm = kr[gbase + jj];
-          if (!(gm & mybits)) continue;   // warp-uniform: the whole warp shares its blocks
-        }
         const SplatRec* r = cur + gbase + jj;
         const float4 q0 = r->q0;
         const float4 q1 = r->q1;
@@ -244,7 +228,6 @@ __device__ __forceinline__ void forward_tile(int tile, int tl, GroupBarrier<256 
         const float tA = q0.z * dx;  // conic pre-scaled by preprocess: pw = A' dx^2 + B' dx dy + C' dy^2 (log2 units)
 #pragma unroll
         for (int i = 0; i < K; i++) {
-          if (K > 1 && !((gm >> (GAB_KEY_BLOCKS_SHIFT + geo.bit(i))) & 1u)) continue;
           const float dy = q0.y - fy[i];
           const float pw = fmaf(q1.x * dy, dy, fmaf(q0.w, dy, tA) * dx);
           const float alpha = fminf(0.99f, q1.y * ex2_approx(pw));
@@ -314,12 +297,10 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
                                                             const float* __restrict__ bg, float* __restrict__ out_color,
                                                             float* __restrict__ final_T,
                                                             uint32_t* __restrict__ n_contrib,
-                                                            uint8_t* __restrict__ strip_mask,
-                                                            const uint32_t* __restrict__ inst_keys) {
+                                                            uint8_t* __restrict__ strip_mask) {
   __shared__ SplatRec buf[2][256];
   __shared__ uint32_t smask[256];
   __shared__ __align__(16) uint32_t ids_ring[4][ID_RING * (64 + 4)];  // per 64-thread group; a 256-thread tile uses it flat
-  __shared__ __align__(16) uint32_t keys_ring[4][ID_RING * (64 + 4)];
   __shared__ __align__(8) uint64_t mbar[4][ID_RING];
   constexpr int GH = KH;  // heavy tiles per CTA (256/KH threads each)
   constexpr int NTH = 256 / KH;
@@ -330,29 +311,27 @@ __global__ void __launch_bounds__(256) blend_forward_kernel(int W, int H, int gx
     const int g = t / NTH, slot = b * GH + g;
     if (slot >= nh) return;
     forward_tile<KH>((int)order[slot], t - g * NTH, GroupBarrier<NTH>{GH == 1 ? 0 : 1 + g}, buf[0] + g * NTH,
-                     buf[1] + g * NTH, smask + g * NTH, &ids_ring[0][0] + g * (ID_RING * (NTH + 4)),
-                     &keys_ring[0][0] + g * (ID_RING * (NTH + 4)), mbar[g], W, H, gx, ranges, point_list, inst_keys, rec,
-                     bg, out_color, final_T, n_contrib, strip_mask);
+                     buf[1] + g * NTH, smask + g * NTH, &ids_ring[0][0] + g * (ID_RING * (NTH + 4)), mbar[g], W, H, gx,
+                     ranges, point_list, rec, bg, out_color, final_T, n_contrib, strip_mask);
   } else {
     const int g = t >> 6, slot = nh + 4 * (b - heavy_ctas) + g;
     if (slot >= tiles) return;
     forward_tile<4>((int)order[slot], t & 63, GroupBarrier<64>{1 + g}, buf[0] + g * 64, buf[1] + g * 64,
-                    smask + g * 64, ids_ring[g], keys_ring[g], mbar[g], W, H, gx, ranges, point_list, inst_keys, rec, bg,
-                    out_color, final_T, n_contrib, strip_mask);
+                    smask + g * 64, ids_ring[g], mbar[g], W, H, gx, ranges, point_list, rec, bg, out_color, final_T,
+                    n_contrib, strip_mask);
   }
 }
 
 void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
                           const uint32_t* point_list, const SplatRec* rec, const float* bg, float* out_color,
-                          float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, const uint32_t* inst_keys,
-                          cudaStream_t stream) {
+                          float* final_T, uint32_t* n_contrib, uint8_t* strip_mask, cudaStream_t stream) {
   const int gx = (W + GAB_TILE - 1) / GAB_TILE, gy = (H + GAB_TILE - 1) / GAB_TILE;
   const int tiles = gx * gy;
   if (tiles == 0) return;
   // upper bound on CTAs: every tile heavy; surplus CTAs exit at once
   const int grid = tiles;
   blend_forward_kernel<1><<<grid, 256, 0, stream>>>(W, H, gx, tiles, ranges, order, order_info, point_list, rec, bg,
-                                                    out_color, final_T, n_contrib, strip_mask, inst_keys);
+                                                    out_color, final_T, n_contrib, strip_mask);
   count_launch();
 }
 

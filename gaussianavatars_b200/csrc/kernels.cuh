@@ -49,69 +49,25 @@ struct TileSpan {
     ystar = (B_ / C_) * dxmax;
   }
   __device__ __forceinline__ float half_width(float dy) const { return sqrtf(fmaxf(0.f, tau2A - det * dy * dy)); }
-  // x-extent [X0, X1] (pixels, margins included) of the accept region over pixel rows with dy in [a, b]; false: empty
-  __device__ __forceinline__ bool extent(float a, float b, float& X0, float& X1) const {
+  __device__ __forceinline__ void row(int ty, int& cx0, int& cx1) const {
+    if (!any) { cx0 = cx1 = rx0; return; }
+    if (full) { cx0 = rx0; cx1 = rx1; return; }
+    const float a = (float)(ty * GAB_TILE) - py, b = a + (float)(GAB_TILE - 1);
     const float lo = fmaxf(a, -ymax) - 0.02f, hi = fminf(b, ymax) + 0.02f;
-    if (lo > hi) return false;
+    if (lo > hi) { cx0 = cx1 = rx0; return; }
     float xr, xl;
     const float hl = half_width(lo), hh = half_width(hi);
     if (-ystar >= lo && -ystar <= hi) xr = dxmax;
     else xr = fmaxf((-B * lo + hl) / A, (-B * hi + hh) / A);
     if (ystar >= lo && ystar <= hi) xl = -dxmax;
     else xl = fminf((-B * lo - hl) / A, (-B * hi - hh) / A);
-    X0 = px + xl - 0.02f;
-    X1 = px + xr + 0.02f;
-    return true;
-  }
-  __device__ __forceinline__ void row(int ty, int& cx0, int& cx1) const {
-    if (!any) { cx0 = cx1 = rx0; return; }
-    if (full) { cx0 = rx0; cx1 = rx1; return; }
-    const float a = (float)(ty * GAB_TILE) - py, b = a + (float)(GAB_TILE - 1);
-    float X0, X1;
-    if (!extent(a, b, X0, X1)) { cx0 = cx1 = rx0; return; }
+    const float X0 = px + xl - 0.02f, X1 = px + xr + 0.02f;
     int t0 = (int)ceilf((X0 - (float)(GAB_TILE - 1)) * (1.0f / GAB_TILE));
     int t1 = (int)floorf(X1 * (1.0f / GAB_TILE)) + 1;
     cx0 = min(max(t0, rx0), rx1);
     cx1 = max(min(t1, rx1), cx0);
   }
-  // The same test one level down: the four 4-row bands of tile row ty (extent per band), then per tile the 8x4-pixel
-  // blocks (bit 2*band + half, half = columns 8h .. 8h+7) whose pixel centres the accept region can reach.  A block
-  // whose bit is clear holds no pixel with alpha >= 1/255 for this splat: the forward blend skips it (blend.cu).
-  struct Bands {
-    float X0[4], X1[4];
-    uint32_t live;  // bands with a non-empty extent; 0x10: every block is live (degenerate conic)
-  };
-  __device__ __forceinline__ Bands bands(int ty) const {
-    Bands r;
-    r.live = 0;
-    if (!any) return r;
-    if (full) { r.live = 0x10u; return r; }
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      const float a = (float)(ty * GAB_TILE + 4 * b) - py;
-      r.X0[b] = r.X1[b] = 0.f;
-      if (extent(a, a + 3.f, r.X0[b], r.X1[b])) r.live |= 1u << b;
-    }
-    return r;
-  }
-  static __device__ __forceinline__ uint32_t block_mask(const Bands& r, int tx) {
-    if (r.live & 0x10u) return 0xffu;
-    const float c0 = (float)(tx * GAB_TILE);
-    uint32_t m = 0;
-#pragma unroll
-    for (int b = 0; b < 4; b++) {
-      if (!((r.live >> b) & 1u)) continue;
-      if (r.X1[b] >= c0 && r.X0[b] <= c0 + 7.f) m |= 1u << (2 * b);
-      if (r.X1[b] >= c0 + 8.f && r.X0[b] <= c0 + 15.f) m |= 2u << (2 * b);
-    }
-    return m;
-  }
 };
-
-// Sorted instance keys: tile id in the low 24 bits (the radix sort looks at those only), the 8-bit block mask of the
-// instance (TileSpan::block_mask) in the high byte -- it rides through the sort for free.
-#define GAB_KEY_TILE_MASK 0x00ffffffu
-#define GAB_KEY_BLOCKS_SHIFT 24
 
 // ---- launchers (each counts its launches) ----
 // Per-splat depth sort as a bucket sort (binning.cu header): bookkeeping arrays in the geometry buffer.
@@ -191,7 +147,7 @@ cudaError_t run_sort(void* temp, size_t temp_bytes, uint32_t* keys_a, uint32_t* 
 void launch_blend_forward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
                           const uint32_t* point_list, const SplatRec* rec,
                           const float* bg, float* out_color, float* final_T, uint32_t* n_contrib, uint8_t* strip_mask,
-                          const uint32_t* inst_keys, cudaStream_t stream);
+                          cudaStream_t stream);
 void launch_blend_backward(int W, int H, const uint2* ranges, const uint32_t* order, const uint32_t* order_info,
                            const uint32_t* point_list, const SplatRec* rec,
                            const float* bg, const float* final_T, const uint32_t* n_contrib, const float* dL_dpix,

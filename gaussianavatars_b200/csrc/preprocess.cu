@@ -492,14 +492,13 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
   // cursor != nullptr (counting tile sort): an instance goes to the next free slot of ITS TILE's segment and carries
   // the splat's depth rank as key; otherwise it goes to offsets[...] + k in emission order with the tile id as key
   // (input of the stable radix sort by tile).
-  auto put = [&](uint32_t o, uint32_t tile, uint32_t blocks, uint32_t rank, uint32_t id) {
-    uint32_t key = tile | (blocks << GAB_KEY_BLOCKS_SHIFT);
+  auto put = [&](uint32_t o, uint32_t tile, uint32_t rank, uint32_t id) {
     if (cursor != nullptr) {
       o = atomicAdd(cursor + tile, 1u);
-      key = rank;
+      tile = rank;
     }
     if (o < cap) {
-      keys[o] = key;
+      keys[o] = tile;
       vals[o] = id;
     }
   };
@@ -541,7 +540,7 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
       const uint32_t sid = __shfl_sync(FULL, i, src);
       for (int t = lane; t < cnt; t += 32) {
         const int y = sy0 + t / w, x = sx0 + t % w;
-        put(soff + t, (uint32_t)(y * gx + x), 0xffu, (uint32_t)(warp_global * 32 + src), sid);
+        put(soff + t, (uint32_t)(y * gx + x), (uint32_t)(warp_global * 32 + src), sid);
       }
     }
     return;
@@ -555,12 +554,9 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
     for (int ty = y0; ty < y1; ty++) {
       int cx0, cx1;
       span.row(ty, cx0, cx1);
-      if (cx1 > cx0) {
-        const TileSpan::Bands bands = span.bands(ty);
-        for (int x = cx0; x < cx1; x++) {
-          put(o, (uint32_t)(ty * gx + x), TileSpan::block_mask(bands, x), (uint32_t)slot, i);
-          o++;
-        }
+      for (int x = cx0; x < cx1; x++) {
+        put(o, (uint32_t)(ty * gx + x), (uint32_t)slot, i);
+        o++;
       }
     }
   }
@@ -588,12 +584,9 @@ __global__ void __launch_bounds__(256) emit_keys_kernel(int P, int gx, int gy, c
         if (lane >= d) incl += nb;
       }
       uint32_t o = base + (uint32_t)(incl - len);
-      if (cx1 > cx0) {
-        const TileSpan::Bands bands = span.bands(ty);
-        for (int x = cx0; x < cx1; x++) {
-          put(o, (uint32_t)(ty * gx + x), TileSpan::block_mask(bands, x), (uint32_t)(warp_global * 32 + src), sid);
-          o++;
-        }
+      for (int x = cx0; x < cx1; x++) {
+        put(o, (uint32_t)(ty * gx + x), (uint32_t)(warp_global * 32 + src), sid);
+        o++;
       }
       base += (uint32_t)__shfl_sync(FULL, incl, 31);
     }
@@ -635,17 +628,17 @@ void launch_emit_keys(int P, int gx, int gy, const SplatRec* rec, const SplatAux
 // =====================================================================================================
 // K5: tile ranges from key transitions in the sorted stream (ranges pre-zeroed by the caller).
 // =====================================================================================================
-// Tile field (low 24 bits of the key) >= tiles: the padding of a capacity-sized sort (sentinel 0xffffffff): they sort behind every real instance
+// Keys >= tiles are the padding of a capacity-sized sort (sentinel 0xffffffff): they sort behind every real instance
 // and all of them land in the spare slot ranges[tiles], which nobody reads.
 __global__ void __launch_bounds__(256) tile_ranges_kernel(int64_t N, uint32_t tiles, const uint32_t* __restrict__ keys,
                                                           uint2* __restrict__ ranges) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= N) return;
-  const uint32_t cur = min(keys[idx] & GAB_KEY_TILE_MASK, tiles);
+  const uint32_t cur = min(keys[idx], tiles);
   if (idx == 0)
     ranges[cur].x = 0;
   else {
-    const uint32_t prev = min(keys[idx - 1] & GAB_KEY_TILE_MASK, tiles);
+    const uint32_t prev = min(keys[idx - 1], tiles);
     if (cur != prev) {
       ranges[prev].y = (uint32_t)idx;
       ranges[cur].x = (uint32_t)idx;
@@ -658,7 +651,7 @@ __global__ void expand_keys_kernel(int64_t N, const uint32_t* __restrict__ tile_
                                    const SplatAux* __restrict__ aux, uint64_t* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  out[i] = ((uint64_t)(tile_keys[i] & GAB_KEY_TILE_MASK) << 32) | (uint64_t)__float_as_uint(aux[ids[i]].depth);
+  out[i] = ((uint64_t)tile_keys[i] << 32) | (uint64_t)__float_as_uint(aux[ids[i]].depth);
 }
 // the reference's key format (tile << 32 | fp32 depth bits) rebuilt from the two-stage sort's outputs (parity export)
 void launch_expand_keys(int64_t N, const uint32_t* tile_keys, const uint32_t* ids, const SplatAux* aux, uint64_t* out,

@@ -424,19 +424,19 @@ enum {
   GAB200_TUNE_DEPTH_SORT = 2,  /* 0 (default): bucket sort when a depth hint is given; 1: always cub radix sort */
   GAB200_TUNE_BWD_VARIANT = 3, /* backward blend schedule (same arithmetic, same results up to summation order):
                                   0 tile = CTA group, live-band-set specialised bodies; 1 warp-independent tasks,
-                                  straight-line bands, pipelined reduction; 2 / 3 (default) as 1 with dead bands
-                                  skipped by uniform branches always / unless all bands are live; 4, 5 = 3, 2 compiled
-                                  for 5 CTAs per SM; 6 = 1 with specialised bodies; 7 = 2 for 6 CTAs per SM.
-                                  Measured at the headline size (profiles/r02/bwd_variants.jsonl): 211 / 198 / 179 /
-                                  175 / 182 / 185 / 186 / 211 us */
+                                  straight-line bands, pipelined reduction; 2 / 3 as 1 with dead bands skipped by
+                                  uniform branches always / unless all bands are live; 4, 5 = 3, 2 compiled for 5 CTAs
+                                  per SM; 6 = 1 with specialised bodies; 7 = 2 for 6 CTAs per SM; 8 (default) = 3 with
+                                  the two bands of a pair in packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2); 9 = 8
+                                  for 5 CTAs per SM.  Measured at the headline size (profiles/r02/bwd_variants.jsonl,
+                                  bwd_packed_variants.jsonl): 211 / 198 / 179 / 175 / 182 / 185 / 186 / 211 / 171 /
+                                  196 us */
   GAB200_TUNE_TILE_SORT = 4,   /* per-instance sort by tile: 0 (default) cub::DeviceRadixSort::SortPairs over the instances
                                   (5 launches + tile-range detection); 1 counting sort by tile + per-tile rank sort
                                   (csrc/tile_sort.cu: 3 launches, no memsets).  Identical sorted streams; at the headline
                                   size the counting form is SLOWER (same-address atomics on the hot tiles' counters:
                                   preprocess +18 us, emission 26 -> 78 us; profiles/r02/tile_sort_counting_vs_cub.json) */
   GAB200_TUNE_NVLS_CTAS = 5,   /* gab200_nvls_allreduce: CTAs of 256 threads (0 = default: 64) */
-  GAB200_TUNE_FWD_BLOCKS = 6,  /* forward blend: 1 (default) skip the (splat, 8x4-pixel block) pairs the emission proved empty
-                                  (block mask in the high byte of the sorted instance key); 0 evaluate every pair */
   GAB200_NUM_TUNABLES = 8
 };
 int32_t gab200_tune(int32_t knob, int32_t value);
