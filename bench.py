@@ -712,7 +712,8 @@ def main():
             traffic = tj.get(dom, {}).get("dram_bytes_per_launch")
             traffic_source = "static: " + str(tj.get(dom, {}).get("source", "committed ncu --set full capture of this workload"))
             if tj.get(dom, {}).get("issue_active_per_cycle") is not None:
-                secondary = {"bound": "issue slots", "issue_active_per_cycle": tj[dom]["issue_active_per_cycle"],
+                secondary = {"bound": "issue slots / fma pipe", "issue_active_per_cycle": tj[dom]["issue_active_per_cycle"],
+                             "fma_pipe_active_pct": tj[dom].get("fma_pipe_active_pct"),
                              "warps_active_per_scheduler": tj[dom].get("warps_active_per_scheduler"),
                              "registers": tj[dom].get("registers"), "source": tj[dom].get("source")}
     except Exception:
