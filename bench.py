@@ -82,6 +82,10 @@ def parse():
                          "graph (two graphs / two buffers used alternately; the K-th reduction is drained inside the timed "
                          "region); sync = the collective sits after backward inside the same graph.  The sync figure is "
                          "measured and reported either way (`sync_collective`)")
+    ap.add_argument("--shard", default="cost", choices=["cost", "round_robin"],
+                    help="N>1 camera sharding: cost = cameras sorted by their instance count (one forward each in warm-up) "
+                         "and dealt so that the cameras of one step have neighbouring costs (dist.shard_frames_by_cost); "
+                         "round_robin = r, r+N, ...")
     ap.add_argument("--splats", type=int, default=None)
     ap.add_argument("--width", type=int, default=None)
     ap.add_argument("--height", type=int, default=None)
@@ -348,7 +352,27 @@ def main():
             symm = bufs[0]
         pc.symm_grad = symm
     cams_host = make_cameras(N_CAMERAS)
-    my_cams = [cams_host[i] for i in gdist.shard_frames(N_CAMERAS, rank, world)] or cams_host
+    shard_note = "all cameras on the one GPU"
+    mine_idx = gdist.shard_frames(N_CAMERAS, rank, world)
+    if world > 1:
+        shard_note = "round robin"
+        if args.shard == "cost" and N_CAMERAS >= world:
+            # one forward per camera (every rank renders all of them once: identical counts), then cost-sorted dealing
+            costs = []
+            with torch.no_grad():
+                for c in cams_host:
+                    pc.update_mesh_properties(syn.pose_mesh(pc.verts_rest, c.timestep).contiguous())
+                    render(c.to(dev), pc, Pipe, torch.ones(3, device=dev))
+                    torch.cuda.synchronize(dev)
+                    costs.append(int(R.last_frame_info().get("num_rendered", 0)))
+            t = torch.tensor(costs, dtype=torch.int64, device=dev)
+            dist.broadcast(t, 0)
+            costs = [int(x) for x in t.tolist()]
+            mine_idx = gdist.shard_frames_by_cost(costs, rank, world)
+            pc.face_center = pc.face_orien_mat = pc.face_scaling = None
+            shard_note = (f"cost-sorted dealing: cameras ordered by instance count ({min(costs)}..{max(costs)}), step j renders "
+                          f"cameras j*{world}..j*{world}+{world - 1} of that order, one per rank")
+    my_cams = [cams_host[i] for i in mine_idx] or cams_host
     cams_dev = [c.to(dev) for c in my_cams]
     # posed meshes (output of the FLAME LBS, upstream of the path) are inputs resident in HBM; the per-face frame
     #  is recomputed inside every step by the library's face-frame kernel
@@ -738,6 +762,7 @@ def main():
                                        "nvls two-shot all-reduce kernel (multimem.ld_reduce + multimem.st) on the "
                                        "symmetric flat buffer, between two signal-pad barriers, inside the graph"),
                    "reduction": "none" if world == 1 else ("deferred by one replay" if deferred else "synchronous"),
+                   "camera_sharding": shard_note,
                    **({"collective_note": collective_note} if collective_note else {}),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
         "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},

@@ -19,6 +19,16 @@ def shard_frames(num_frames: int, rank: int, world_size: int) -> List[int]:
     return list(range(rank, num_frames, world_size))
 
 
+def shard_frames_by_cost(costs: Sequence[float], rank: int, world_size: int) -> List[int]:
+    """Cost-aware sharding: cameras sorted by a cost estimate (the instance count of a previous visit), then dealt out
+    so that the cameras rendered in the SAME step -- positions j*W .. j*W + W-1 of the sorted list -- have neighbouring
+    costs.  A synchronous data-parallel step lasts as long as its slowest rank; with frames of unequal cost, dealing
+    neighbours to one step makes every step cost about its group's mean instead of the maximum over a random draw
+    (the sequence-length bucketing of other domains).  Every camera still goes to exactly one rank."""
+    order = sorted(range(len(costs)), key=lambda i: (costs[i], i))
+    return order[rank::world_size]
+
+
 def _flat_covers(flat: torch.Tensor, grads: Sequence[torch.Tensor]) -> bool:
     if flat is None:
         return False

@@ -95,6 +95,21 @@ def test_frame_sharding_is_a_partition():
     assert gdist.shard_frames(3, 5, 8) == []
 
 
+def test_cost_sorted_dealing_is_a_partition_with_neighbouring_costs_per_step():
+    from gaussianavatars_b200 import dist as gdist
+
+    costs = [530, 910, 100, 740, 745, 300, 120, 905, 610, 615, 290, 101, 999, 500, 480, 770]
+    for world in (1, 2, 4, 8):
+        shards = [gdist.shard_frames_by_cost(costs, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(len(costs)))            # every camera exactly once
+        assert len({len(s) for s in shards}) == 1
+        order = sorted(range(len(costs)), key=lambda i: (costs[i], i))
+        for j in range(len(costs) // world):                                  # step j = a run of the sorted order
+            assert sorted(s[j] for s in shards) == sorted(order[j * world:(j + 1) * world])
+    # ties are broken by index: deterministic on every rank
+    assert gdist.shard_frames_by_cost([5, 5, 5, 5], 1, 2) == [1, 3]
+
+
 def test_two_rank_sharded_grads_equal_single_rank_accumulation(tmp_path):
     port = 29500 + (os.getpid() % 2000)
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
