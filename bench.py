@@ -82,7 +82,10 @@ def parse():
                          "graph (two graphs / two buffers used alternately; the K-th reduction is drained inside the timed "
                          "region); sync = the collective sits after backward inside the same graph.  The sync figure is "
                          "measured and reported either way (`sync_collective`)")
-    ap.add_argument("--shard", default="cost", choices=["cost", "round_robin"],
+    ap.add_argument("--side-at", default="start", choices=["start", "backward"],
+                    help="deferred reduction: fork the reduction branch at the start of the frame or after its forward")
+    ap.add_argument("--nvls-ctas", type=int, default=0, help="CTAs of the two-shot NVLS kernel (0 = library default)")
+    ap.add_argument("--shard", default="round_robin", choices=["cost", "round_robin"],
                     help="N>1 camera sharding: cost = cameras sorted by their instance count (one forward each in warm-up) "
                          "and dealt so that the cameras of one step have neighbouring costs (dist.shard_frames_by_cost); "
                          "round_robin = r, r+N, ...")
@@ -307,6 +310,8 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
     N.lib()
+    if args.nvls_ctas > 0:
+        N.tune(N.TUNE_NVLS_CTAS, args.nvls_ctas)
     R.set_exact_binning(args.exact_binning)
     R.keep_last_state(True)
 
@@ -504,7 +509,7 @@ def main():
                               warm_cameras=cam_blocks_dev[:n_common])
             fr.set_inputs(camera=cam_blocks_dev[0], verts=posed[0].detach(), dL_dimage=gout)
             pair.append(fr)
-        pair_with_deferred_reduce(pair, bufs)
+        pair_with_deferred_reduce(pair, bufs, side_work_at=args.side_at)
         for fr in pair:
             fr.capture()
         return pair
@@ -583,7 +588,7 @@ def main():
         e2e_frames[0].prefetch_for(e2e_frames[1])
         e2e_frames[1].prefetch_for(e2e_frames[0])
         if deferred:   # each graph's forked branch also all-reduces the other frame's gradient buffer
-            pair_with_deferred_reduce(e2e_frames, bufs)
+            pair_with_deferred_reduce(e2e_frames, bufs, side_work_at=args.side_at)
         for f_ in e2e_frames:
             f_.capture()
         done = [torch.cuda.Event() for _ in range(2)]
@@ -763,6 +768,7 @@ def main():
                                        "symmetric flat buffer, between two signal-pad barriers, inside the graph"),
                    "reduction": "none" if world == 1 else ("deferred by one replay" if deferred else "synchronous"),
                    "camera_sharding": shard_note,
+                   **({"reduction_branch": f"forked at {args.side_at}, nvls ctas {args.nvls_ctas or 'default'}"} if deferred else {}),
                    **({"collective_note": collective_note} if collective_note else {}),
                    "l2": "flushed between steps (256 MiB fill outside the per-step event pair)"},
         "warm_l2": {"value": world * K / (ms_warm / 1e3), "unit": "frames/s", "ms_per_step": ms_warm / K},

@@ -52,7 +52,7 @@ def camera_block(cam) -> torch.Tensor:
                       cam.camera_center.reshape(-1).float()))
 
 
-def pair_with_deferred_reduce(frames, buffers):
+def pair_with_deferred_reduce(frames, buffers, side_work_at: str = "start"):
     """Two frames of one model used alternately, each with its own caller-owned gradient buffer
     (dist.SymmetricGradBuffer, mode "two_shot" or "plain"): frame k's backward fills buffers[k], and a forked branch of
     frame k's graph all-reduces buffers[1-k] -- the gradients of the PREVIOUS step -- while frame k computes.  After
@@ -72,6 +72,7 @@ def pair_with_deferred_reduce(frames, buffers):
         f.before_backward = before
         f.after_backward = lambda mine=mine: mine.end(reduce=False)
         f.side_work = other.reduce
+        f.side_work_at = side_work_at
         if f._side is None:
             f._side = torch.cuda.Stream(device=f.device)
     return frames
@@ -87,7 +88,7 @@ class GraphedFrame:
     def __init__(self, pc, width: int, height: int, fovx: float, fovy: float, bg: torch.Tensor, loss: str = "l1_u8",
                  lambda_dssim: float = 0.2, host_inputs: bool = False, capacity: Optional[int] = None,
                  headroom: float = 1.25, after_backward=None, warm_cameras=None, regularizers: Optional[dict] = None,
-                 before_backward=None, side_work=None):
+                 before_backward=None, side_work=None, side_work_at: str = "start"):
         """loss: "l1_u8" (L1 vs a uint8 ground truth), "photometric" ((1-l) L1 + l (1-SSIM) vs a uint8 ground truth) or
         "dL_dimage" (the caller supplies dL/dimage in `self.dL_dimage`).
         host_inputs: the frame owns pinned STAGING tensors (`cam_stage` (35,) float32, `gt_stage` (3,H,W) uint8) that a
@@ -115,6 +116,7 @@ class GraphedFrame:
         self.after_backward = after_backward
         self.before_backward = before_backward   # e.g. SymmetricGradBuffer.begin
         self.side_work = side_work
+        self.side_work_at = side_work_at   # "start": beside the whole frame; "backward": forked after the forward
         self.regularizers = regularizers
         if regularizers is not None and loss == "dL_dimage":
             raise ValueError("regularizers need a scalar loss ('l1_u8' or 'photometric')")
@@ -211,7 +213,7 @@ class GraphedFrame:
                     other.cam.copy_(other.cam_stage, non_blocking=True)
                     if other.gt_stage is not None:
                         other.gt.copy_(other.gt_stage, non_blocking=True)
-                if self.side_work is not None:
+                if self.side_work is not None and self.side_work_at == "start":
                     self.side_work()
         pc.update_mesh_properties(self.verts)
         out = render(self.camera, pc, _Pipe, self.bg)
@@ -222,11 +224,13 @@ class GraphedFrame:
                 lx, ls = binding_regularizers(pc._xyz, pc._scaling, out["radii"], getattr(pc, "binding", None),
                                               getattr(pc, "face_scaling", None), **self.regularizers)
                 loss = loss + lx + ls
+            self._fork_side_at_backward()
             if self.before_backward is not None:
                 self.before_backward()
             loss.backward()
         else:
             loss = None
+            self._fork_side_at_backward()
             if self.before_backward is not None:
                 self.before_backward()
             img.backward(self.dL_dimage)
@@ -238,6 +242,12 @@ class GraphedFrame:
         if forked:   # join the branch (a captured fork must end inside the graph)
             torch.cuda.current_stream(self.device).wait_stream(self._side)
         self.image, self.radii, self.viewspace_points = img.detach(), out["radii"], out["viewspace_points"]
+
+    def _fork_side_at_backward(self):
+        if self.side_work is not None and self.side_work_at == "backward":
+            self._side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(self._side):
+                self.side_work()
 
     # ---- capture ---------------------------------------------------------------------------------------------------
     def _learn_capacity(self):
